@@ -1,0 +1,698 @@
+// nlos_oracle.cpp — CPU ORACLE for the differentiable confocal transient renderer.
+//
+// *** TEST INFRASTRUCTURE, NOT PRODUCT. ***  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.  The product (libnlos_b200.so) never
+// links, imports or calls anything in oracle/.
+//
+// *** PARITY UNPINNED. ***  This is a restatement of the reference's algorithm, written from
+// SURVEY.md Appendix A and the reference sources cited below.  The reference itself cannot be built in
+// this image (needs Embree 3 incl. internal headers, Intel MKL VSL, TBB, Boost.Random — none present,
+// none pinned by the reference) and it ships no golden vectors, so this oracle cannot be checked against
+// reference outputs.  It is checked instead against closed-form cases, brute-force-vs-BVH agreement and
+// term-by-term finite differences (tests/test_oracle_*.py).
+//
+// What is restated (file:line relative to /root/reference/transient_rendering_cython/):
+//   forward task          smoothed_transient/transient_and_gradient.cpp:122-237   (GGX: ggx/transient_and_gradient.cpp:126-243)
+//   forward driver+smooth smoothed_transient/transient_and_gradient.cpp:271-376
+//   orchestration / diff  smoothed_transient/stratifiedStreamedGradientRenderer.cpp:514-572
+//   gradient driver/task  smoothed_transient/transient_and_gradient.cpp:506-569, 843-1007 (GGX: ggx/...:581-645, 648-823)
+//   albedo scalar         smoothed_transient/transient_and_gradient.cpp:441-503, 571-695
+//   alpha scalar          ggx/transient_and_gradient.cpp:385-512, 514-577
+//   intensity             smoothed_transient/transient_and_gradient.cpp:22-119, 239-267
+//   per-bin vertex grad   smoothed_transient/transient_and_gradient.cpp:379-439, 697-840
+//   mesh regularisers     smoothed_transient/stratifiedStreamedGradientRenderer.cpp:27-180
+//   GGX BRDF              ggx/ggx_confocal.cpp:13-231
+//   bits -> float         smoothed_transient/rng_sse.h:33-42
+//
+// Deliberate, documented departures (SURVEY.md A.6 "F" rows):
+//   * RNG: the reference's per-thread SFMT streams make samples depend on TBB scheduling.  Here the two
+//     uniforms of sample k of (source s, triangle f) are Philox4x32-10(key=seed, ctr=(f, s, k>>1, 0)),
+//     words {0,1} for even k and {2,3} for odd k, mapped to [0,1) with the reference's 23-bit trick.
+//   * Embree's rtcIntersect1M is restated as: nearest hit over all triangles, Moeller-Trumbore in
+//     Embree's edge form (C=v0-o, R=C x d, den=Ng.d, U=R.e2, V=R.e1, T=Ng.C), no back-face culling,
+//     t in (0,inf), ties broken towards the LOWEST primitive index (order independent).
+//   * float expression order / fused multiply-adds are pinned (the reference is built -Ofast, so it has
+//     no defined rounding): dot(a,b)=fma(a.z,b.z,fma(a.y,b.y,a.x*b.x)), cross(a,b).x=fma(a.y,b.z,-(a.z*b.y)),
+//     blend(u,v,w)=fma(w,c,fma(v,b,u*a)); IEEE sqrt and divide.  Compile with -ffp-contract=off.
+//   * out-of-range bins (reference: out-of-bounds read/write) are skipped; numBins is passed explicitly.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -mfma -fopenmp).
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <limits>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct V3 { float x, y, z; };
+static inline V3 mk(float x, float y, float z) { V3 r{x, y, z}; return r; }
+static inline V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+static inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+static inline V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+static inline V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+static inline float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline V3 cross3(V3 a, V3 b) {
+  return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+static inline float len3(V3 a) { return sqrtf(dot3(a, a)); }
+static inline V3 blend3(float u, V3 a, float v, V3 b, float w, V3 c) {
+  return mk(fmaf(w, c.x, fmaf(v, b.x, u * a.x)), fmaf(w, c.y, fmaf(v, b.y, u * a.y)), fmaf(w, c.z, fmaf(v, b.z, u * a.z)));
+}
+static inline float blend1(float u, float a, float v, float b, float w, float c) { return fmaf(w, c, fmaf(v, b, u * a)); }
+static inline V3 ld3(const float* p, int64_t i) { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+static inline void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// rng_sse.h:33-42: uniform in [1,2) from 23 mantissa bits, minus 1
+static inline float bits_to_unit(uint32_t x) {
+  union { uint32_t u; float f; } c; c.u = (x >> 9) | 0x3f800000u; return c.f - 1.0f;
+}
+static inline void sample_ST(uint64_t seed, int64_t src, int tri, int k, float& S, float& T) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)tri, (uint32_t)src, (uint32_t)(k >> 1), (uint32_t)((uint64_t)src >> 32), o);
+  if (k & 1) { S = bits_to_unit(o[2]); T = bits_to_unit(o[3]); } else { S = bits_to_unit(o[0]); T = bits_to_unit(o[1]); }
+}
+
+// ---------------------------------------------------------------- triangle in Embree's TriangleM form
+struct TriRec { V3 v0, e1, e2, Ng; };   // e1=v0-v1, e2=v2-v0, Ng=cross(e2,e1)
+static inline TriRec make_tri(V3 a, V3 b, V3 c) { TriRec t; t.v0 = a; t.e1 = a - b; t.e2 = c - a; t.Ng = cross3(t.e2, t.e1); return t; }
+
+// Moeller-Trumbore, Embree edge form, division only on a valid hit. Returns true and (t,u,v) with
+// p = (1-u-v) v0 + u v1 + v v2.
+static inline bool isect(const TriRec& tr, V3 o, V3 d, float& t, float& u, float& v) {
+  V3 C = tr.v0 - o;
+  V3 R = cross3(C, d);
+  float den = dot3(tr.Ng, d);
+  float absDen = fabsf(den);
+  float sgn = den < 0.0f ? -1.0f : 1.0f;
+  float U = dot3(R, tr.e2) * sgn;
+  float V = dot3(R, tr.e1) * sgn;
+  float T = dot3(tr.Ng, C) * sgn;
+  if (!(den != 0.0f) || !(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= absDen) || !(T > 0.0f)) return false;
+  t = T / absDen; u = U / absDen; v = V / absDen;
+  return true;
+}
+
+// ---------------------------------------------------------------- BVH (object-median split, <=4 tris/leaf)
+struct Box { V3 lo, hi; };
+struct Node { Box b; int left, right, first, count; };   // count>0 => leaf over order[first..first+count)
+
+struct Scene {
+  int F = 0, V = 0;
+  const float* verts = nullptr; const int32_t* faces = nullptr;
+  std::vector<TriRec> tris;
+  std::vector<Node> nodes; std::vector<int> order;
+  bool brute = false;
+  float pad = 0.f;
+};
+
+static Box tri_box(const Scene& sc, int f) {
+  V3 a = ld3(sc.verts, sc.faces[3 * f]), b = ld3(sc.verts, sc.faces[3 * f + 1]), c = ld3(sc.verts, sc.faces[3 * f + 2]);
+  Box r;
+  r.lo = mk(std::min(a.x, std::min(b.x, c.x)) - sc.pad, std::min(a.y, std::min(b.y, c.y)) - sc.pad, std::min(a.z, std::min(b.z, c.z)) - sc.pad);
+  r.hi = mk(std::max(a.x, std::max(b.x, c.x)) + sc.pad, std::max(a.y, std::max(b.y, c.y)) + sc.pad, std::max(a.z, std::max(b.z, c.z)) + sc.pad);
+  return r;
+}
+static Box merge(Box a, Box b) {
+  Box r; r.lo = mk(std::min(a.lo.x, b.lo.x), std::min(a.lo.y, b.lo.y), std::min(a.lo.z, b.lo.z));
+  r.hi = mk(std::max(a.hi.x, b.hi.x), std::max(a.hi.y, b.hi.y), std::max(a.hi.z, b.hi.z)); return r;
+}
+static int build_rec(Scene& sc, std::vector<Box>& boxes, std::vector<V3>& cent, int first, int count) {
+  int id = (int)sc.nodes.size(); sc.nodes.push_back(Node());
+  Box b = boxes[sc.order[first]];
+  for (int i = 1; i < count; ++i) b = merge(b, boxes[sc.order[first + i]]);
+  sc.nodes[id].b = b;
+  if (count <= 4) { sc.nodes[id].left = sc.nodes[id].right = -1; sc.nodes[id].first = first; sc.nodes[id].count = count; return id; }
+  V3 clo = cent[sc.order[first]], chi = clo;
+  for (int i = 1; i < count; ++i) { V3 c = cent[sc.order[first + i]]; clo = mk(std::min(clo.x, c.x), std::min(clo.y, c.y), std::min(clo.z, c.z)); chi = mk(std::max(chi.x, c.x), std::max(chi.y, c.y), std::max(chi.z, c.z)); }
+  V3 e = chi - clo; int ax = (e.x >= e.y && e.x >= e.z) ? 0 : (e.y >= e.z ? 1 : 2);
+  int mid = count / 2;
+  auto key = [&](int t) { const V3& c = cent[t]; return ax == 0 ? c.x : (ax == 1 ? c.y : c.z); };
+  std::nth_element(sc.order.begin() + first, sc.order.begin() + first + mid, sc.order.begin() + first + count,
+                   [&](int a, int bb) { float ka = key(a), kb = key(bb); return ka < kb || (ka == kb && a < bb); });
+  int l = build_rec(sc, boxes, cent, first, mid);
+  int r = build_rec(sc, boxes, cent, first + mid, count - mid);
+  sc.nodes[id].left = l; sc.nodes[id].right = r; sc.nodes[id].first = 0; sc.nodes[id].count = 0;
+  return id;
+}
+static void build_scene(Scene& sc, const float* verts, int V, const int32_t* faces, int F, const float* origins, int64_t L, bool brute) {
+  sc.F = F; sc.V = V; sc.verts = verts; sc.faces = faces; sc.brute = brute;
+  sc.tris.resize(F);
+  float scale = 0.f;
+  for (int i = 0; i < 3 * V; ++i) scale = std::max(scale, fabsf(verts[i]));
+  for (int64_t i = 0; i < 3 * L; ++i) scale = std::max(scale, fabsf(origins[i]));
+  sc.pad = scale * (1.0f / 65536.0f);   // conservative: float edge tests are wrong by << 1e-6*scale
+  for (int f = 0; f < F; ++f) sc.tris[f] = make_tri(ld3(verts, faces[3 * f]), ld3(verts, faces[3 * f + 1]), ld3(verts, faces[3 * f + 2]));
+  if (brute || F == 0) return;
+  std::vector<Box> boxes(F); std::vector<V3> cent(F);
+  for (int f = 0; f < F; ++f) { boxes[f] = tri_box(sc, f); cent[f] = (boxes[f].lo + boxes[f].hi) * 0.5f; }
+  sc.order.resize(F); for (int f = 0; f < F; ++f) sc.order[f] = f;
+  sc.nodes.reserve(2 * (size_t)F);
+  build_rec(sc, boxes, cent, 0, F);
+}
+
+struct Hit { int prim; float t, u, v; };
+struct TraceStats { uint64_t rays = 0, box = 0, tri = 0; };
+
+static inline bool box_hit(const Box& b, V3 o, V3 id, float tbest, float& tnear) {
+  float tx1 = (b.lo.x - o.x) * id.x, tx2 = (b.hi.x - o.x) * id.x;
+  float ty1 = (b.lo.y - o.y) * id.y, ty2 = (b.hi.y - o.y) * id.y;
+  float tz1 = (b.lo.z - o.z) * id.z, tz2 = (b.hi.z - o.z) * id.z;
+  float tmn = std::max(std::max(std::min(tx1, tx2), std::min(ty1, ty2)), std::max(std::min(tz1, tz2), 0.0f));
+  float tmx = std::min(std::min(std::max(tx1, tx2), std::max(ty1, ty2)), std::max(tz1, tz2));
+  tnear = tmn;
+  // relaxed: boxes are padded, and a tie on t must still reach the lower-index primitive
+  return tmn <= tmx * 1.0000005f && tmn <= tbest * 1.0000005f;
+}
+static inline float safe_rcp(float x) { const float tiny = 1e-20f; if (fabsf(x) < tiny) x = (x < 0.f || (x == 0.f && std::signbit(x))) ? -tiny : tiny; return 1.0f / x; }
+
+// nearest hit: lexicographic min of (t, prim) over all valid intersections
+static Hit nearest_hit(const Scene& sc, V3 o, V3 d, TraceStats* st) {
+  Hit best; best.prim = -1; best.t = std::numeric_limits<float>::infinity(); best.u = best.v = 0.f;
+  auto consider = [&](int f) {
+    float t, u, v;
+    if (st) st->tri++;
+    if (isect(sc.tris[f], o, d, t, u, v)) {
+      if (t < best.t || (t == best.t && f < best.prim)) { best.prim = f; best.t = t; best.u = u; best.v = v; }
+    }
+  };
+  if (st) st->rays++;
+  if (sc.brute) { for (int f = 0; f < sc.F; ++f) consider(f); return best; }
+  if (sc.nodes.empty()) return best;
+  V3 id = mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  int stack[128]; int sp = 0; float tn;
+  if (st) st->box++;
+  if (!box_hit(sc.nodes[0].b, o, id, best.t, tn)) return best;
+  stack[sp++] = 0;
+  while (sp) {
+    const Node& n = sc.nodes[stack[--sp]];
+    if (n.count > 0) { for (int i = 0; i < n.count; ++i) consider(sc.order[n.first + i]); continue; }
+    float tl, tr; if (st) st->box += 2;
+    bool hl = box_hit(sc.nodes[n.left].b, o, id, best.t, tl);
+    bool hr = box_hit(sc.nodes[n.right].b, o, id, best.t, tr);
+    if (hl && hr) { if (tl <= tr) { stack[sp++] = n.right; stack[sp++] = n.left; } else { stack[sp++] = n.left; stack[sp++] = n.right; } }
+    else if (hl) stack[sp++] = n.left;
+    else if (hr) stack[sp++] = n.right;
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------- GGX (ggx/ggx_confocal.cpp), x = n.w
+static inline float ggx_D(float a, float nw) {                     // :29-49
+  if (nw <= 0) return 0.0f;
+  float nw2 = nw * nw;
+  float be = (1.0f - nw2) / (a * a) / nw2;
+  float root = (1.0f + be) * nw2;
+  float result = (float)(1.0f / (M_PI * a * a * root * root));
+  if (result * nw < 1e-20f) result = 0;
+  return result;
+}
+static inline float ggx_G1(float a, float nw) {                    // :56-70
+  if (nw <= 0) return 0.0f;
+  if (nw >= 1.0f || nw <= -1.0f) return 1.0f;
+  float root = a * a + (1.0f - a * a) * nw * nw;
+  return 2.0f / (nw + sqrtf(root));
+}
+static inline float ggx_G(float a, float nw) { float g = ggx_G1(a, nw); return g * g; }
+static inline float ggx_eval(float a, V3 n, V3 w) {                // :13-27
+  float nw = dot3(n, w);
+  if (nw <= 0) return 0.0f;
+  float Dv = ggx_D(a, nw); if (Dv == 0) return 0.0f;
+  return Dv * ggx_G(a, nw) / 4.0f;
+}
+static inline float ggx_D_adiff(float a, float nw) {               // :100-113
+  if (nw <= 0) return 0.0f;
+  float nw2 = nw * nw, a2 = a * a, val = a2 * nw2 - nw2 + 1;
+  return (float)(-(2.0f * a * (a2 * nw2 + nw2 - 1)) / (M_PI * val * val * val));
+}
+static inline float ggx_G1_adiff(float a, float nw) {              // :119-136
+  if (nw <= 0) return 0.0f;
+  if (nw >= 1.0f || nw <= -1.0f) return 0.0f;
+  float nw2 = nw * nw;
+  float val = sqrtf(a * a - nw2 * (a * a - 1));
+  float root = nw + val;
+  return 2.0f * a * (nw2 - 1.0f) / (val * root * root);
+}
+static inline float ggx_eval_adiff(float a, V3 n, V3 w) {          // :74-98
+  float nw = dot3(n, w);
+  if (nw <= 0) return 0.0f;
+  float Dv = ggx_D(a, nw); if (Dv == 0) return 0.0f;
+  float Gv = ggx_G(a, nw);
+  float Dp = ggx_D_adiff(a, nw);
+  float Gp = 2.0f * ggx_G1_adiff(a, nw) * ggx_G1(a, nw);
+  return (Dp * Gv + Gp * Dv) / 4.0f;
+}
+static inline float ggx_D_ndiff(float a, float nw) {               // :195-207
+  if (nw <= 0) return 0.0f;
+  float nw2 = nw * nw, a2 = a * a, root = (a2 - 1.0f) * nw2 + 1.0f;
+  return (float)(-(4.0f * a2 * nw * (a2 - 1.0f)) / (M_PI * root * root * root));
+}
+static inline float ggx_G1_ndiff(float a, float nw) {              // :213-231
+  if (nw <= 0) return 0.0f;
+  if (nw >= 1.0f || nw <= -1.0f) return 0.0f;
+  float nw2 = nw * nw, a2 = a * a;
+  float temp = sqrtf(a2 - nw2 * (a2 - 1.0f));
+  float root = nw + temp;
+  return -2.0f * (1.0f - (nw * (a2 - 1.0f)) / temp) / root / root;
+}
+// :138-166 ; the reference leaves dn/dw uninitialised on early return -> zero here (A.6 "F")
+static inline void ggx_eval_nwdiff(float a, V3 n, V3 w, V3& dn, V3& dw) {
+  dn = mk(0, 0, 0); dw = mk(0, 0, 0);
+  float nw = dot3(n, w);
+  if (nw <= 0) return;
+  float Dv = ggx_D(a, nw); if (Dv == 0) return;
+  float Gv = ggx_G(a, nw);
+  float Gp = 2.0f * ggx_G1_ndiff(a, nw) * ggx_G1(a, nw);
+  float Dp = ggx_D_ndiff(a, nw);
+  float sc = (Dp * Gv + Gp * Dv) / 4.0f;
+  dn = sc * w; dw = sc * n;
+}
+
+// ---------------------------------------------------------------- per-call parameters
+struct Params {
+  const float* origin; const float* onormal; int64_t L; int64_t src_offset;
+  const float* verts; int V; const int32_t* faces; int F;
+  const float* vnormal; const float* valbedo;
+  float alpha;        // < 0 => Lambertian (smoothed_transient/), >= 0 => GGX (ggx/)
+  int num_samples; float lb, ub, res; int numBins;
+  uint64_t seed;
+};
+static inline int spp_of(const Params& p) { return 1 + (p.num_samples - 1) / p.F; }   // TG.cpp:289
+
+struct TriSetup {           // TG.cpp:146-173
+  int i1, i2, i3; V3 v1, v2, v3, nf, n1, n2, n3; float A, a1, a2, a3;
+};
+static inline TriSetup setup_tri(const Params& p, int f) {
+  TriSetup s; s.i1 = p.faces[3 * f]; s.i2 = p.faces[3 * f + 1]; s.i3 = p.faces[3 * f + 2];
+  s.v1 = ld3(p.verts, s.i1); s.v2 = ld3(p.verts, s.i2); s.v3 = ld3(p.verts, s.i3);
+  V3 N = cross3(s.v2 - s.v1, s.v3 - s.v1);
+  s.A = len3(N) / 2; s.nf = N / (2 * s.A);
+  s.n1 = s.n2 = s.n3 = mk(0, 0, 1);
+  if (p.vnormal) { s.n1 = ld3(p.vnormal, s.i1); s.n2 = ld3(p.vnormal, s.i2); s.n3 = ld3(p.vnormal, s.i3); }
+  s.a1 = s.a2 = s.a3 = 1.f;
+  if (p.valbedo) { s.a1 = p.valbedo[s.i1]; s.a2 = p.valbedo[s.i2]; s.a3 = p.valbedo[s.i3]; }
+  return s;
+}
+
+// One stratified sample: generate (TG.cpp:184-195), trace (:199), visibility + re-derived point (:206-215).
+struct Sample { bool visible; bool in_range; float u, v, w, r; V3 d; };
+static inline Sample trace_sample(const Scene& sc, const Params& p, const TriSetup& ts, int f, int64_t s_local, int k, TraceStats* st) {
+  Sample sm; sm.visible = false; sm.in_range = false;
+  float S, T; sample_ST(p.seed, p.src_offset + s_local, f, k, S, T);
+  float sqrtT = sqrtf(T);
+  float u = 1 - sqrtT, v = (1 - S) * sqrtT, w = S * sqrtT;
+  V3 o = ld3(p.origin, s_local);
+  V3 point = blend3(u, ts.v1, v, ts.v2, w, ts.v3);
+  V3 q = point - o;
+  float inv = 1.0f / len3(q);
+  V3 d = q * inv;
+  sm.d = d;
+  Hit h = nearest_hit(sc, o, d, st);
+  if (h.prim != f) return sm;
+  sm.visible = true;
+  sm.v = h.u; sm.w = h.v; sm.u = 1.0f - sm.v - sm.w;
+  V3 pt = blend3(sm.u, ts.v1, sm.v, ts.v2, sm.w, ts.v3);
+  sm.r = len3(pt - o);
+  sm.in_range = (sm.r <= p.ub / 2.0f) && (sm.r >= p.lb / 2.0f);
+  return sm;
+}
+static inline V3 shading_normal(const Params& p, const TriSetup& ts, const Sample& sm) {
+  return p.vnormal ? blend3(sm.u, ts.n1, sm.v, ts.n2, sm.w, ts.n3) : ts.nf;
+}
+static inline float shading_albedo(const Params& p, const TriSetup& ts, const Sample& sm) {
+  return p.valbedo ? blend1(sm.u, ts.a1, sm.v, ts.a2, sm.w, ts.a3) : 1.0f;
+}
+
+// Gaussian taps (TG.cpp:537-544 / :350-355)
+struct Taps { int K; std::vector<double> w; double sigma, sigma2; };
+static Taps make_taps(float res, int r, int s) {
+  Taps t; t.K = 4 * r * s + 1; t.w.resize(t.K);
+  t.sigma = res * s / 2.355; t.sigma2 = t.sigma * t.sigma;
+  double norm = 1 / t.sigma / sqrt(2 * M_PI) * res / r;
+  for (int i = 0; i < t.K; ++i) { double x = (-2 * r * s + i) * res / r / t.sigma; t.w[i] = exp(-(x * x) / 2) * norm; }
+  return t;
+}
+
+// ---------------------------------------------------------------- forward (TG.cpp:271-376)
+static void render_transients(const Scene& sc, const Params& p, int r, int s, double* transient, TraceStats* stats, uint8_t* vis) {
+  const int spp = spp_of(p); const int B = p.numBins; const int64_t nbf = (int64_t)B * r;
+  const float res_eff = p.res / r;                                 // :313
+  std::memset(transient, 0, sizeof(double) * p.L * B);
+  std::vector<double> fine; double* acc = transient;
+  if (r > 1) { fine.assign((size_t)p.L * nbf, 0.0); acc = fine.data(); }
+  uint64_t nr = 0, nb = 0, nt = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nr, nb, nt)
+  for (int64_t src = 0; src < p.L; ++src) {                         // one source row per task => no write races
+    TraceStats st; V3 o_n = ld3(p.onormal, src);
+    double* row = acc + src * nbf;
+    for (int f = 0; f < p.F; ++f) {
+      TriSetup ts = setup_tri(p, f);
+      for (int k = 0; k < spp; ++k) {
+        Sample sm = trace_sample(sc, p, ts, f, src, k, stats ? &st : nullptr);
+        if (vis) vis[((size_t)src * p.F + f) * spp + k] = sm.visible ? 1 : 0;
+        if (!sm.visible || !sm.in_range) continue;
+        V3 n = shading_normal(p, ts, sm); float alb = shading_albedo(p, ts, sm);
+        float ff = -dot3(n, sm.d) * dot3(o_n, sm.d) / sm.r / sm.r;     // :224-227
+        ff = std::max(0.0f, ff);                                    // :228 (clamps the product)
+        int64_t bin = (int64_t)floorf((2.0f * sm.r - p.lb) / res_eff);   // :229
+        if (bin < 0 || bin >= nbf) continue;                        // reference: out-of-bounds write
+        float val = ts.A * alb * ff * ff;
+        if (p.alpha >= 0) val = val * ggx_eval(p.alpha, n, -sm.d);  // ggx/TG.cpp:236-238
+        row[bin] += (double)val / (double)spp;                      // :231-232
+      }
+    }
+    nr += st.rays; nb += st.box; nt += st.tri;
+  }
+  if (stats) { stats->rays += nr; stats->box += nb; stats->tri += nt; }
+  if (r == 1) return;
+  // :348-371 Gaussian smoothing at the refined resolution, then sum r fine bins per coarse bin
+  Taps tp = make_taps(p.res, r, s); const int K = tp.K, half = 2 * r * s;
+#pragma omp parallel for schedule(static)
+  for (int64_t src = 0; src < p.L; ++src) {
+    std::vector<double> y((size_t)nbf + 4 * r * s, 0.0);
+    const double* x = fine.data() + src * nbf;
+    for (int64_t m = 0; m < nbf; ++m) { double xv = x[m]; if (xv == 0.0) continue; for (int i = 0; i < K; ++i) y[m + i] += tp.w[i] * xv; }   // full conv (convolution_mkl.cpp:3-11)
+    for (int64_t m = 0; m < nbf; ++m) transient[src * B + m / r] += y[m + half];
+  }
+}
+
+static void fill_pathlengths(const Params& p, double* pathlengths) {   // SST.cpp:126-129
+  if (!pathlengths) return;
+  for (int i = 0; i < p.numBins; ++i) pathlengths[i] = (double)(p.lb + i * p.res);
+}
+static void make_difference(const Params& p, const double* data, const double* weight, const double* transient, int loss_flag, std::vector<double>& diff) {  // SSG.cpp:543-550
+  size_t n = (size_t)p.L * p.numBins; diff.resize(n);
+  for (size_t i = 0; i < n; ++i) { double d = data[i] - transient[i]; if (loss_flag == 1) d = 2 * d * d * d; diff[i] = d * weight[i]; }
+}
+
+// ---------------------------------------------------------------- vertex gradient (TG.cpp:506-569, 843-1007; GGX 648-823)
+static void render_gradients(const Scene& sc, const Params& p, int r, int s, const double* diff, double* gradient, int testing_flag) {
+  const int spp = spp_of(p); const int B = p.numBins; Taps tp = make_taps(p.res, r, s);
+  const size_t G = (size_t)3 * p.V;
+  int nth = 1;
+#ifdef _OPENMP
+  nth = omp_get_max_threads();
+#endif
+  std::vector<double> accs((size_t)nth * G, 0.0);
+#pragma omp parallel
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    double* g_acc = accs.data() + (size_t)tid * G;
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t src = 0; src < p.L; ++src) {
+      V3 o_n = ld3(p.onormal, src);
+      for (int f = 0; f < p.F; ++f) {
+        TriSetup ts = setup_tri(p, f);
+        for (int k = 0; k < spp; ++k) {
+          Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+          if (!sm.visible || !sm.in_range) continue;
+          V3 n = shading_normal(p, ts, sm); float alb = shading_albedo(p, ts, sm);
+          V3 d = sm.d; float hl = sm.r;
+          float c2 = dot3(o_n, d), c3 = dot3(n, -d);                 // :944-947
+          if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+          float ff = c2 * c3 / hl / hl;
+          V3 t1, gn = mk(0, 0, 0); double intensity;
+          if (p.alpha < 0) {
+            intensity = alb * ff * ff;                               // :950
+            t1 = (2 * alb * c2 * c3) * (o_n * c3 - n * c2 + (4 * (-d)) * c2 * c3);   // :953
+            t1 = t1 / powf(hl, 5);                                    // :954
+            if (testing_flag == 0 && p.vnormal) {                    // :959-964
+              gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / powf(hl, 4);
+              float ct = dot3(gn, n); gn = gn - n * ct;
+            }
+          } else {                                                    // ggx/TG.cpp:756-780
+            float brdf = ggx_eval(p.alpha, n, -d);
+            V3 dn, dw; ggx_eval_nwdiff(p.alpha, n, -d, dn, dw);
+            V3 dx = -dw + d * dot3(d, dw) / hl;                       // :759 (sic: only 2nd term / r)
+            intensity = alb * ff * ff * brdf;
+            V3 t11 = (2 * c2 * c3) * (o_n * c3 - n * c2 + (4 * (-d)) * c2 * c3);
+            t11 = t11 / powf(hl, 5); t11 = t11 * brdf;
+            V3 t12 = (ff * ff) * dx;
+            t1 = t11 + t12;
+            if (testing_flag == 0 && p.vnormal) {
+              gn = (-2 * d) * c3 * c2 * c2 * brdf; gn = gn / powf(hl, 4);
+              gn = gn + (ff * ff) * dn;
+              float ct = dot3(gn, n); gn = gn - n * ct;
+            }
+          }
+          V3 t2 = n * (float)intensity;                               // :956
+          t2 = (t2 + gn) / (2 * ts.A);                                // :966
+          const V3 e1 = ts.v3 - ts.v2, e2 = ts.v1 - ts.v3, e3 = ts.v2 - ts.v1;
+          const V3 x1 = cross3(t2, e1), x2 = cross3(t2, e2), x3 = cross3(t2, e3);
+          for (int i = 0; i < tp.K; ++i) {                            // :972-1001
+            double delta = (double)(((float)(-2 * r * s + i) * p.res) / (float)r);
+            V3 gg = (float)(delta / tp.sigma2 * 2) * d;
+            int64_t bin = (int64_t)floor(((double)(2.0f * hl) + delta - (double)p.lb) / (double)p.res);
+            if (bin < 0 || bin >= B) continue;                        // reference: out-of-bounds read
+            float wk = (float)tp.w[i], df = (float)((-2) * diff[src * B + bin]);
+            V3 base = t1 + gg * (float)intensity;
+            V3 g;
+            g = base * sm.u + x1; g = g * wk; g = g * df;
+            g_acc[3 * ts.i1] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i1 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i1 + 2] += (double)(ts.A * g.z) / (double)spp;
+            g = base * sm.v + x2; g = g * wk; g = g * df;
+            g_acc[3 * ts.i2] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i2 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i2 + 2] += (double)(ts.A * g.z) / (double)spp;
+            g = base * sm.w + x3; g = g * wk; g = g * df;
+            g_acc[3 * ts.i3] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i3 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i3 + 2] += (double)(ts.A * g.z) / (double)spp;
+          }
+        }
+      }
+    }
+  }
+  for (int t = 0; t < nth; ++t) for (size_t d = 0; d < G; ++d) gradient[d] += accs[(size_t)t * G + d] / (double)p.L;   // :561-565 ('+=' into caller's array)
+}
+
+// scalar gradients: albedo (TG.cpp:571-695, 441-503) and GGX alpha (ggx/TG.cpp:385-512, 514-577)
+static double render_scalar_gradient(const Scene& sc, const Params& p, int r, int s, const double* diff, bool wrt_alpha) {
+  const int spp = spp_of(p); const int B = p.numBins; Taps tp = make_taps(p.res, r, s);
+  double total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+  for (int64_t src = 0; src < p.L; ++src) {
+    V3 o_n = ld3(p.onormal, src); double acc = 0;
+    for (int f = 0; f < p.F; ++f) {
+      TriSetup ts = setup_tri(p, f);
+      for (int k = 0; k < spp; ++k) {
+        Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+        if (!sm.visible || !sm.in_range) continue;
+        V3 n = shading_normal(p, ts, sm); float alb = shading_albedo(p, ts, sm);
+        V3 d = sm.d; float hl = sm.r;
+        float c2 = dot3(o_n, d), c3 = dot3(n, -d);
+        if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+        float ff = c2 * c3 / hl / hl;
+        double g0;
+        if (wrt_alpha) g0 = alb * ff * ff * ggx_eval_adiff(p.alpha, n, -d);   // ggx/TG.cpp:492-493
+        else g0 = ff * ff;                                                    // TG.cpp:677 (no albedo factor)
+        for (int i = 0; i < tp.K; ++i) {
+          double delta = (double)(((float)(-2 * r * s + i) * p.res) / (float)r);
+          int64_t bin = (int64_t)floor(((double)(2.0f * hl) + delta - (double)p.lb) / (double)p.res);
+          if (bin < 0 || bin >= B) continue;
+          if (wrt_alpha) acc += (double)ts.A * g0 * tp.w[i] * (-2) * diff[src * B + bin] / (double)spp;   // ggx/TG.cpp:505
+          else { double g = g0 * tp.w[i] * (-2) * diff[src * B + bin]; acc += (double)(ts.A * g) / (double)spp; }   // TG.cpp:687-688
+        }
+      }
+    }
+    total += acc;
+  }
+  return total / (double)p.L;
+}
+
+// per-triangle intensity (TG.cpp:22-119; GGX ggx/TG.cpp:20-125)
+static void render_intensity(const Scene& sc, const Params& p, double* intensity) {
+  const int spp = spp_of(p);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int f = 0; f < p.F; ++f) {                                   // one triangle per task => no write races
+    TriSetup ts = setup_tri(p, f); double acc = 0;
+    for (int64_t src = 0; src < p.L; ++src) {
+      V3 o_n = ld3(p.onormal, src);
+      for (int k = 0; k < spp; ++k) {
+        Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+        if (!sm.visible || !sm.in_range) continue;
+        V3 n = shading_normal(p, ts, sm);
+        float ff = -dot3(n, sm.d) * dot3(o_n, sm.d) / sm.r / sm.r; ff = std::max(0.0f, ff);
+        float val = ts.A * 1.0f * ff * ff;
+        if (p.alpha >= 0) val = val * ggx_eval(p.alpha, n, -sm.d);
+        acc += (double)val / (double)spp;
+      }
+    }
+    intensity[f] += acc;
+  }
+}
+
+// per-bin gradient of one vertex (debug/figure; TG.cpp:379-439, 697-840); always includes gn with face normals
+static void render_vertex_gradient(const Scene& sc, const Params& p, int r, int s, int vertex_num, double* gradient /*[B,3]*/) {
+  const int spp = spp_of(p); const int B = p.numBins; Taps tp = make_taps(p.res, r, s);
+  std::vector<double> acc((size_t)3 * B, 0.0);
+  for (int64_t src = 0; src < p.L; ++src) {
+    V3 o_n = ld3(p.onormal, src);
+    for (int f = 0; f < p.F; ++f) {
+      TriSetup ts = setup_tri(p, f);
+      if (ts.i1 != vertex_num && ts.i2 != vertex_num && ts.i3 != vertex_num) continue;
+      for (int k = 0; k < spp; ++k) {
+        Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+        if (!sm.visible || !sm.in_range) continue;
+        V3 n = ts.nf, d = sm.d; float alb = 1.f, hl = sm.r;
+        float c2 = dot3(o_n, d), c3 = dot3(n, -d); if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+        float ff = c2 * c3 / hl / hl; double intensity = alb * ff * ff;
+        V3 t1 = (2 * alb * c2 * c3) * (o_n * c3 - n * c2 + (4 * (-d)) * c2 * c3); t1 = t1 / powf(hl, 5);
+        V3 gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / powf(hl, 4); float ct = dot3(gn, n); gn = gn - n * ct;
+        V3 t2 = n * (float)intensity; t2 = (t2 + gn) / (2 * ts.A);
+        for (int i = 0; i < tp.K; ++i) {
+          double delta = (double)(((float)(-2 * r * s + i) * p.res) / (float)r);
+          V3 gg = (float)(delta / tp.sigma2 * 2) * d;
+          int64_t bin = (int64_t)floor(((double)(2.0f * hl) + delta - (double)p.lb) / (double)p.res);
+          if (bin < 0 || bin >= B) continue;
+          V3 e; float bk;
+          if (vertex_num == ts.i1) { e = ts.v3 - ts.v2; bk = sm.u; } else if (vertex_num == ts.i2) { e = ts.v1 - ts.v3; bk = sm.v; } else { e = ts.v2 - ts.v1; bk = sm.w; }
+          V3 g = (t1 + gg * (float)intensity) * bk + cross3(t2, e); g = g * (float)tp.w[i];
+          acc[3 * bin] += (double)(ts.A * g.x) / (double)spp; acc[3 * bin + 1] += (double)(ts.A * g.y) / (double)spp; acc[3 * bin + 2] += (double)(ts.A * g.z) / (double)spp;
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < acc.size(); ++i) gradient[i] += acc[i] / (double)p.L;
+}
+
+static Params make_params(const float* origin, int64_t L, const float* onormal, const float* verts, int V, const float* vn, const float* va,
+                          const int32_t* faces, int F, float alpha, int num_samples, float lb, float ub, float res, int numBins, uint64_t seed, int64_t src_offset) {
+  Params p; p.origin = origin; p.onormal = onormal; p.L = L; p.src_offset = src_offset; p.verts = verts; p.V = V; p.faces = faces; p.F = F;
+  p.vnormal = vn; p.valbedo = va; p.alpha = alpha; p.num_samples = num_samples; p.lb = lb; p.ub = ub; p.res = res; p.numBins = numBins; p.seed = seed;
+  return p;
+}
+
+}  // namespace
+
+// ==================================================================================== C ABI (tests only)
+extern "C" {
+
+struct nlos_oracle_stats { uint64_t rays, box_tests, tri_tests; };
+
+// mode bit0: brute-force nearest hit (no BVH)
+int nlos_oracle_transient(const float* origin, int64_t L, const float* onormal, const float* verts, int V, const float* vnormal, const float* valbedo,
+                          const int32_t* faces, int F, float alpha, int num_samples, float lb, float ub, float res, int numBins,
+                          double* transient, double* pathlengths, int refine_scale, int sigma_bin, uint64_t seed, int64_t src_offset, int mode,
+                          uint8_t* visibility /*nullable [L,F,spp]*/, nlos_oracle_stats* stats /*nullable*/) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, valbedo, faces, F, alpha, num_samples, lb, ub, res, numBins, seed, src_offset);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  TraceStats st;
+  render_transients(sc, p, refine_scale, sigma_bin, transient, stats ? &st : nullptr, visibility);
+  if (stats) { stats->rays = st.rays; stats->box_tests = st.box; stats->tri_tests = st.tri; }
+  return 0;
+}
+
+// kind: 0 vertex gradient -> gradient[V,3] (+=);  1 albedo scalar;  2 GGX alpha scalar.  Returns the scalar via *scalar_out.
+int nlos_oracle_gradient(const double* data, const double* weight, const float* origin, int64_t L, const float* onormal, const float* verts, int V,
+                         const float* vnormal, const float* valbedo, const int32_t* faces, int F, float alpha, int num_samples, float lb, float ub, float res,
+                         int numBins, double* transient, double* pathlengths, double* gradient, int refine_scale, int sigma_bin, int testing_flag, int loss_flag,
+                         uint64_t seed, int64_t src_offset, int mode, int kind, double* scalar_out) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, valbedo, faces, F, alpha, num_samples, lb, ub, res, numBins, seed, src_offset);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  int r_fwd = sigma_bin < 5 ? 1 : refine_scale;                       // SSG.cpp:521-524
+  render_transients(sc, p, r_fwd, sigma_bin, transient, nullptr, nullptr);
+  std::vector<double> diff; make_difference(p, data, weight, transient, loss_flag, diff);
+  if (kind == 0) render_gradients(sc, p, refine_scale, sigma_bin, diff.data(), gradient, testing_flag);
+  else { double g = render_scalar_gradient(sc, p, refine_scale, sigma_bin, diff.data(), kind == 2); if (scalar_out) *scalar_out = g; }
+  return 0;
+}
+
+int nlos_oracle_intensity(const float* origin, int64_t L, const float* onormal, const float* verts, int V, const float* vnormal, const int32_t* faces, int F,
+                          float alpha, int num_samples, float lb, float ub, double* intensity, uint64_t seed, int64_t src_offset, int mode) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, nullptr, faces, F, alpha, num_samples, lb, ub, 1.0f, 1, seed, src_offset);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  render_intensity(sc, p, intensity);
+  return 0;
+}
+
+int nlos_oracle_vertex_gradient(int vertex_num, const float* origin, int64_t L, const float* onormal, const float* verts, int V, const int32_t* faces, int F,
+                                int num_samples, float lb, float ub, float res, int numBins, double* gradient, int refine_scale, int sigma_bin, uint64_t seed, int mode) {
+  Params p = make_params(origin, L, onormal, verts, V, nullptr, nullptr, faces, F, -1.f, num_samples, lb, ub, res, numBins, seed, 0);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  render_vertex_gradient(sc, p, refine_scale, sigma_bin, vertex_num, gradient);
+  return 0;
+}
+
+// smoothed_transient/stratifiedStreamedGradientRenderer.cpp:125-160.  The reference writes the per-vertex
+// gradient with '=' from every adjacent face (last writer wins, racy); restated serially in face order.
+double nlos_oracle_normal_smoothing(const float* verts, int V, const int32_t* faces, int F, const int32_t* aff, double* grad) {
+  std::vector<double> nrm((size_t)3 * F), area(F);
+  for (int f = 0; f < F; ++f) {
+    V3 a = ld3(verts, faces[3 * f]), b = ld3(verts, faces[3 * f + 1]), c = ld3(verts, faces[3 * f + 2]);
+    V3 N = cross3(b - a, c - a); float A = len3(N) / 2; area[f] = A; N = N / (2 * A);
+    nrm[3 * f] = N.x; nrm[3 * f + 1] = N.y; nrm[3 * f + 2] = N.z;
+  }
+  std::memset(grad, 0, sizeof(double) * 3 * V);
+  double value = 0;
+  for (int f = 0; f < F; ++f) {
+    V3 n = mk((float)nrm[3 * f], (float)nrm[3 * f + 1], (float)nrm[3 * f + 2]); V3 fn = n;
+    n = n * (float)area[f];
+    for (int i = 0; i < 3; ++i) { int g = aff[3 * f + i]; if (g < 0) continue; V3 n1 = mk((float)nrm[3 * g], (float)nrm[3 * g + 1], (float)nrm[3 * g + 2]); n = n + n1 * (float)area[g]; }
+    n = n / len3(n);
+    value += area[f] * (1 - dot3(n, fn));
+    fn = fn - n;
+    int i1 = faces[3 * f], i2 = faces[3 * f + 1], i3 = faces[3 * f + 2];
+    V3 v1 = ld3(verts, i1), v2 = ld3(verts, i2), v3 = ld3(verts, i3);
+    V3 g = cross3(fn, (v3 - v2) / 2); grad[3 * i1] = g.x; grad[3 * i1 + 1] = g.y; grad[3 * i1 + 2] = g.z;
+    g = cross3(fn, (v1 - v3) / 2); grad[3 * i2] = g.x; grad[3 * i2 + 1] = g.y; grad[3 * i2 + 2] = g.z;
+    g = cross3(fn, (v2 - v1) / 2); grad[3 * i3] = g.x; grad[3 * i3 + 1] = g.y; grad[3 * i3 + 2] = g.z;
+  }
+  return value;
+}
+// :27-57, 162-180 ('=' per face, then summed over threads; restated serially in face order)
+void nlos_oracle_curvature_grad(const float* verts, int V, const int32_t* faces, int F, double* grad) {
+  std::memset(grad, 0, sizeof(double) * 3 * V);
+  for (int f = 0; f < F; ++f) {
+    int i1 = faces[3 * f], i2 = faces[3 * f + 1], i3 = faces[3 * f + 2];
+    V3 v1 = ld3(verts, i1), v2 = ld3(verts, i2), v3 = ld3(verts, i3);
+    V3 N = cross3(v2 - v1, v3 - v1); float A = len3(N) / 2; N = N / (2 * A);
+    V3 g = cross3(N, (v3 - v2) / 2); grad[3 * i1] = g.x; grad[3 * i1 + 1] = g.y; grad[3 * i1 + 2] = g.z;
+    g = cross3(N, (v1 - v3) / 2); grad[3 * i2] = g.x; grad[3 * i2 + 1] = g.y; grad[3 * i2 + 2] = g.z;
+    g = cross3(N, (v2 - v1) / 2); grad[3 * i3] = g.x; grad[3 * i3 + 1] = g.y; grad[3 * i3 + 2] = g.z;
+  }
+}
+
+// helpers exported for unit tests
+void nlos_oracle_philox(uint64_t seed, int64_t src, int tri, int k, float* S, float* T) { sample_ST(seed, src, tri, k, *S, *T); }
+int nlos_oracle_isect(const float* v /*9*/, const float* o, const float* d, float* tuv) {
+  TriRec tr = make_tri(ld3(v, 0), ld3(v, 1), ld3(v, 2)); float t, u, w;
+  bool h = isect(tr, ld3(o, 0), ld3(d, 0), t, u, w); if (h) { tuv[0] = t; tuv[1] = u; tuv[2] = w; } return h ? 1 : 0;
+}
+float nlos_oracle_ggx(int which, float alpha, const float* n, const float* w, float* dn, float* dw) {
+  V3 N = ld3(n, 0), W = ld3(w, 0);
+  if (which == 0) return ggx_eval(alpha, N, W);
+  if (which == 1) return ggx_eval_adiff(alpha, N, W);
+  V3 a, b; ggx_eval_nwdiff(alpha, N, W, a, b); dn[0] = a.x; dn[1] = a.y; dn[2] = a.z; dw[0] = b.x; dw[1] = b.y; dw[2] = b.z; return 0.f;
+}
+void nlos_oracle_taps(float res, int r, int s, double* w /*4rs+1*/, double* sigma2) { Taps t = make_taps(res, r, s); std::memcpy(w, t.w.data(), sizeof(double) * t.K); *sigma2 = t.sigma2; }
+int nlos_oracle_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
