@@ -1,0 +1,147 @@
+/* nlos_b200.h — C ABI of libnlos_b200.so, the B200 (sm_100a) drop-in for the reference's differentiable
+ * confocal transient renderer.
+ *
+ * Each nlos_streamed_* entry point replaces one C++ function that the reference's Cython modules
+ * `renderer` (smoothed_transient/renderer.pyx) and `ggx` (ggx/ggx.pyx) bind.  Argument order and meaning
+ * are the reference's, with three additions: a leading context handle, an `int` status return (0 = ok;
+ * the reference returns void and only printf()s on failure), and an explicit trailing `numBins`
+ * (the reference recomputes ceil((ub-lb)/res) in float on both sides of the boundary; passing it removes
+ * the row-misalignment quirk of SURVEY.md A.6).  Scalar results come back through an out-pointer.
+ *
+ * Citations are relative to /root/reference/transient_rendering_cython/.
+ *
+ * Pointers: every array argument may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
+ * context's GPU, independently per argument (detected with cudaPointerGetAttributes).  Host arrays are
+ * staged to HBM inside the call and results copied back before it returns; device arrays are used in
+ * place and the call returns after enqueueing on the context stream (use nlos_ctx_synchronize).
+ * Layouts are the reference's: C-contiguous, float = f32, int = i32, double = f64;
+ * `transient` [L,B] is overwritten, `gradient` [V,3] is accumulated into ("+=", TG.cpp:563).
+ *
+ * Sampling: the two uniforms of sample k of (source s, triangle f) are
+ * Philox4x32-10(key = seed, counter = (f, s_global, k>>1, 0)) -> reference bit trick (rng_sse.h:33-42);
+ * the default seed is 5489, the reference's built-in boost::mt19937 default (sampler.cpp:25).
+ *
+ * There is no CPU fallback: every entry point fails with NLOS_ERR_CUDA if no sm_100-class device is usable.
+ */
+#ifndef NLOS_B200_H_
+#define NLOS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nlos_ctx nlos_ctx;
+
+enum {
+  NLOS_OK = 0,
+  NLOS_ERR_INVALID = 1,   /* bad argument (null pointer, non-positive size, numBins mismatch ...) */
+  NLOS_ERR_CUDA = 2,      /* CUDA runtime error; text in nlos_last_error() */
+  NLOS_ERR_NOMEM = 3      /* device allocation failed (reference: printf("memory insufficient"), TG.cpp:302-305) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int nlos_ctx_create(int device, nlos_ctx** out);
+void nlos_ctx_destroy(nlos_ctx* ctx);
+const char* nlos_last_error(nlos_ctx* ctx);            /* ctx may be NULL: error of the last failed create */
+int nlos_ctx_synchronize(nlos_ctx* ctx);
+void* nlos_ctx_stream(nlos_ctx* ctx);                  /* the cudaStream_t all work is enqueued on */
+int nlos_ctx_set_seed(nlos_ctx* ctx, uint64_t seed);
+/* Sharded runs (one process per GPU): this call's sources are the global sources
+ * [src_offset, src_offset + numSources); gradients are normalised by num_sources_global (0 = by numSources). */
+int nlos_ctx_set_source_window(nlos_ctx* ctx, int64_t src_offset, int64_t num_sources_global);
+/* keys: "reuse_visibility" (1), "chunk_forward" (0 = auto), "chunk_gradient" (0 = auto), "timing" (0) */
+int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value);
+/* ms of the last call: {scene build, forward, residual, gradient, total}; needs option "timing" = 1 */
+int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5);
+uint64_t nlos_ctx_launch_count(nlos_ctx* ctx);         /* kernels launched through this context so far */
+
+/* ---- module `renderer` (smoothed_transient/) ----------------------------------------------------- */
+
+/* smoothed_transient/stratifiedStreamedTransientRenderer.h:5  streamed_render_transient
+ * (renderer.pyx:175 renderStreamedTransient, :139 ...Shading, :157 ...wAlbedo) */
+int nlos_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                   const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                   const float* vertexAlbedo /*nullable*/, const int* trianglesD, int numTriangles,
+                                   int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                   float pathlengthResolution, double* transient, double* pathlengths,
+                                   int refine_scale, int sigma_bin, int numBins);
+
+/* smoothed_transient/stratifiedStreamedTransientRenderer.h:3  streamed_render_intensity
+ * (renderer.pyx:191 renderStreamedTriangleIntensity); intensity[F] is accumulated into */
+int nlos_streamed_render_intensity(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                   const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                   const int* trianglesD, int numTriangles, int numSamples,
+                                   float pathlengthLowerBound, float pathlengthUpperBound, double* intensity);
+
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:7  streamed_render_gradient
+ * (renderer.pyx:94 renderStreamedGradient, :116 renderStreamedShadingGradient) */
+int nlos_streamed_render_gradient(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                  int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                  const float* vertexNormal /*nullable*/, const int* trianglesD, int numTriangles,
+                                  int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                  float pathlengthResolution, double* transient, double* pathlengths, double* gradient,
+                                  int refine_scale, int sigma_bin, int testing_flag, int loss_test, int numBins);
+
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:5  streamed_render_gradient_w_albedo
+ * (renderer.pyx:55 renderStreamedGradientWithAlbedo) */
+int nlos_streamed_render_gradient_w_albedo(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                           int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                           const float* albedo, const int* trianglesD, int numTriangles, int numSamples,
+                                           float pathlengthLowerBound, float pathlengthUpperBound, float pathlengthResolution,
+                                           double* transient, double* pathlengths, double* gradient, int refine_scale,
+                                           int sigma_bin, int testing_flag, int loss_test, int numBins);
+
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:3  streamed_render_gradient_albedo
+ * (renderer.pyx:35 renderStreamedGradientAlbedo); the reference returns the double */
+int nlos_streamed_render_gradient_albedo(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                         int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                         const float* albedo, const int* trianglesD, int numTriangles, int numSamples,
+                                         float pathlengthLowerBound, float pathlengthUpperBound, float pathlengthResolution,
+                                         double* transient, double* pathlengths, int refine_scale, int sigma_bin,
+                                         int testing_flag, int loss_test, int numBins, double* result /*host*/);
+
+/* ---- module `ggx` (ggx/) -------------------------------------------------------------------------- */
+
+/* ggx/stratifiedStreamedTransientRenderer.h:4  streamed_render_transient (ggx.pyx:118, :82, :100) */
+int nlos_ggx_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                       const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                       const float* vertexAlbedo /*nullable*/, const int* trianglesD, int numTriangles,
+                                       float alpha, int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                       float pathlengthResolution, double* transient, double* pathlengths,
+                                       int refine_scale, int sigma_bin, int numBins);
+
+/* ggx/stratifiedStreamedTransientRenderer.h:3  streamed_render_intensity (ggx.pyx:134) */
+int nlos_ggx_streamed_render_intensity(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                       const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                       const int* trianglesD, int numTriangles, float alpha, int numSamples,
+                                       float pathlengthLowerBound, float pathlengthUpperBound, double* intensity);
+
+/* ggx/stratifiedStreamedGradientRenderer.h:6  streamed_render_gradient (ggx.pyx:37, :59); no loss_test */
+int nlos_ggx_streamed_render_gradient(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                      int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                      const float* vertexNormal /*nullable*/, const int* trianglesD, int numTriangles,
+                                      float alpha, int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                      float pathlengthResolution, double* transient, double* pathlengths, double* gradient,
+                                      int refine_scale, int sigma_bin, int testing_flag, int numBins);
+
+/* ggx/stratifiedStreamedGradientRenderer.h:4  streamed_render_gradient_alpha (ggx.pyx:12) */
+int nlos_ggx_streamed_render_gradient_alpha(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                            int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                            const float* vertexNormal /*nullable*/, const int* trianglesD, int numTriangles,
+                                            float alpha, int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                            float pathlengthResolution, double* transient, double* pathlengths,
+                                            int refine_scale, int sigma_bin, int numBins, double* result /*host*/);
+
+/* ---- test / profiling hooks ------------------------------------------------------------------------ */
+
+/* Pure-geometry per-sample visibility (nearest hit == sampled triangle, TG.cpp:206) as bytes [L,F,spp];
+ * counters (nullable, host) = {rays traced, box tests, triangle tests}. */
+int nlos_debug_visibility(nlos_ctx* ctx, const float* originD, int numSources, const float* verticesD, int numVertices,
+                          const int* trianglesD, int numTriangles, int numSamples, uint8_t* visibility, uint64_t* counters3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLOS_B200_H_ */

@@ -1,0 +1,148 @@
+"""ctypes loader for libnlos_b200.so (the C ABI of include/nlos_b200.h).
+
+The shared library is built in-tree by `make -C nlos_surface_optimization_b200/csrc` (or
+`__graft_entry__.build()`).  There is no fallback: if the library is missing, or no B200-class GPU is
+usable, importing works but creating a context raises NlosError loudly.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnlos_b200.so')
+
+NLOS_OK, NLOS_ERR_INVALID, NLOS_ERR_CUDA, NLOS_ERR_NOMEM = 0, 1, 2, 3
+
+
+class NlosError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+_f = C.POINTER(C.c_float)
+_d = C.POINTER(C.c_double)
+_i = C.POINTER(C.c_int)
+_ctx = C.c_void_p
+
+# every symbol declared in include/nlos_b200.h with its argument types (tests/test_abi_symbols.py
+# cross-checks this table against the header)
+SIGNATURES = {
+    'nlos_ctx_create': (C.c_int, [C.c_int, C.POINTER(_ctx)]),
+    'nlos_ctx_destroy': (None, [_ctx]),
+    'nlos_last_error': (C.c_char_p, [_ctx]),
+    'nlos_ctx_synchronize': (C.c_int, [_ctx]),
+    'nlos_ctx_stream': (C.c_void_p, [_ctx]),
+    'nlos_ctx_set_seed': (C.c_int, [_ctx, C.c_uint64]),
+    'nlos_ctx_set_source_window': (C.c_int, [_ctx, C.c_int64, C.c_int64]),
+    'nlos_ctx_set_option': (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
+    'nlos_ctx_get_timing': (C.c_int, [_ctx, _f]),
+    'nlos_ctx_launch_count': (C.c_uint64, [_ctx]),
+    'nlos_streamed_render_transient': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                 _d, _d, C.c_int, C.c_int, C.c_int]),
+    'nlos_streamed_render_intensity': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, _d]),
+    'nlos_streamed_render_gradient': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                _d, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'nlos_streamed_render_gradient_w_albedo': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                         C.c_float, _d, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'nlos_streamed_render_gradient_albedo': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                       C.c_float, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _d]),
+    'nlos_ggx_streamed_render_transient': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                                     C.c_float, _d, _d, C.c_int, C.c_int, C.c_int]),
+    'nlos_ggx_streamed_render_intensity': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, _d]),
+    'nlos_ggx_streamed_render_gradient': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                                    C.c_float, _d, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'nlos_ggx_streamed_render_gradient_alpha': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float,
+                                                          C.c_float, C.c_float, _d, _d, C.c_int, C.c_int, C.c_int, _d]),
+    'nlos_debug_visibility': (C.c_int, [_ctx, _f, C.c_int, _f, C.c_int, _i, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
+}
+
+
+def load_library(path=None):
+    """dlopen the C ABI and attach argtypes.  Raises NlosError if the library has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise NlosError('%s not found: build it with `make -C %s` (there is no CPU fallback)' % (p, os.path.join(_HERE, 'csrc')))
+        lib = C.CDLL(p)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here = header/library mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if path is None:
+            _lib = lib
+        return lib
+
+
+class Context(object):
+    """Owns one nlos_ctx (stream + scratch buffers) on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _ctx()
+        rc = self.lib.nlos_ctx_create(int(device), C.byref(h))
+        if rc != NLOS_OK:
+            msg = self.lib.nlos_last_error(None)
+            raise NlosError('nlos_ctx_create(device=%d) failed (%d): %s' % (device, rc, msg.decode() if msg else '?'))
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc, what):
+        if rc != NLOS_OK:
+            msg = self.lib.nlos_last_error(self.handle)
+            raise NlosError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+    def set_seed(self, seed):
+        self.check(self.lib.nlos_ctx_set_seed(self.handle, int(seed)), 'nlos_ctx_set_seed')
+
+    def set_source_window(self, src_offset, num_sources_global):
+        self.check(self.lib.nlos_ctx_set_source_window(self.handle, int(src_offset), int(num_sources_global)), 'nlos_ctx_set_source_window')
+
+    def set_option(self, key, value):
+        self.check(self.lib.nlos_ctx_set_option(self.handle, key.encode(), int(value)), 'nlos_ctx_set_option(%s)' % key)
+
+    def synchronize(self):
+        self.check(self.lib.nlos_ctx_synchronize(self.handle), 'nlos_ctx_synchronize')
+
+    def timing(self):
+        buf = (C.c_float * 5)()
+        self.check(self.lib.nlos_ctx_get_timing(self.handle, buf), 'nlos_ctx_get_timing')
+        return dict(zip(('build_ms', 'forward_ms', 'residual_ms', 'gradient_ms', 'total_ms'), [float(x) for x in buf]))
+
+    def launch_count(self):
+        return int(self.lib.nlos_ctx_launch_count(self.handle))
+
+    @property
+    def stream(self):
+        return self.lib.nlos_ctx_stream(self.handle)
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.nlos_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """One lazily created context per device; device defaults to LOCAL_RANK (one process per GPU) or 0."""
+    if device is None:
+        device = int(os.environ.get('NLOS_B200_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+    with _lock:
+        ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _default_ctx[device] = ctx
+    return ctx

@@ -1,0 +1,313 @@
+// nlos_core.cuh — per-thread building blocks of the B200 transient renderer.
+//
+// Everything here is a pure function of its arguments (no threadIdx, no shared memory), so the same
+// code can be instantiated inside the sm_100a kernels and, for logic checks only, inside a host test
+// harness (tests/emul).  The library is compiled with -fmad=false: an FMA happens exactly where fmaf()
+// is written, '/' and sqrtf() are IEEE — that is what makes per-sample visibility and bin indices
+// bit-identical to the CPU oracle (DESIGN.md "Arithmetic contract").
+//
+// Reference formulas (relative to /root/reference/transient_rendering_cython/):
+//   sampling / visibility / binning   smoothed_transient/transient_and_gradient.cpp:184-232
+//   gradient terms                    smoothed_transient/transient_and_gradient.cpp:944-1001
+//   GGX                               ggx/ggx_confocal.cpp:13-231, ggx/transient_and_gradient.cpp:756-780
+//   bits -> [0,1)                     smoothed_transient/rng_sse.h:33-42
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define NLOS_HD __host__ __device__ __forceinline__
+#else
+#define NLOS_HD inline
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace nlos {
+
+// ------------------------------------------------------------------ tiny vector algebra (pinned op order)
+struct f3 { float x, y, z; };
+NLOS_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+NLOS_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+NLOS_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+NLOS_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+NLOS_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+NLOS_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+NLOS_HD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+NLOS_HD float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+NLOS_HD f3 cross3(f3 a, f3 b) {
+  return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+NLOS_HD float len3(f3 a) { return sqrtf(dot3(a, a)); }
+NLOS_HD f3 blend3(float u, f3 a, float v, f3 b, float w, f3 c) {
+  return mk3(fmaf(w, c.x, fmaf(v, b.x, u * a.x)), fmaf(w, c.y, fmaf(v, b.y, u * a.y)), fmaf(w, c.z, fmaf(v, b.z, u * a.z)));
+}
+NLOS_HD float blend1(float u, float a, float v, float b, float w, float c) { return fmaf(w, c, fmaf(v, b, u * a)); }
+NLOS_HD f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+
+NLOS_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  union { float f; int i; } c; c.f = f; return c.i;
+#endif
+}
+NLOS_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  union { float f; int i; } c; c.i = i; return c.f;
+#endif
+}
+
+// ------------------------------------------------------------------ counter-based RNG: Philox4x32-10
+NLOS_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+NLOS_HD float bits_to_unit(uint32_t x) { return i2f((int)((x >> 9) | 0x3f800000u)) - 1.0f; }
+
+// the two uniforms of sample k of (global source index src, original triangle index tri)
+NLOS_HD void sample_ST(uint64_t seed, int64_t src, int tri, int k, float& S, float& T) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)tri, (uint32_t)src, (uint32_t)(k >> 1), (uint32_t)((uint64_t)src >> 32), o);
+  if (k & 1) { S = bits_to_unit(o[2]); T = bits_to_unit(o[3]); } else { S = bits_to_unit(o[0]); T = bits_to_unit(o[1]); }
+}
+
+// ------------------------------------------------------------------ triangle records (device layout, 64 B each)
+// TraceTri (4 x float4): [v0.xyz | prim] [e1.xyz | -] [e2.xyz | -] [Ng.xyz | -]   e1=v0-v1, e2=v2-v0, Ng=cross(e2,e1)
+// ShadeTri (4 x float4): [v1.xyz | A] [v2.xyz | nf.x] [v3.xyz | nf.y] [nf.z | i1 | i2 | i3]
+struct TriRec { f3 v0, e1, e2, Ng; };
+NLOS_HD TriRec make_tri(f3 a, f3 b, f3 c) { TriRec t; t.v0 = a; t.e1 = a - b; t.e2 = c - a; t.Ng = cross3(t.e2, t.e1); return t; }
+
+// Moeller-Trumbore in Embree's edge form; division only on a valid hit.  p = (1-u-v) v0 + u v1 + v v2.
+NLOS_HD bool isect(const TriRec& tr, f3 o, f3 d, float& t, float& u, float& v) {
+  const f3 C = tr.v0 - o;
+  const f3 R = cross3(C, d);
+  const float den = dot3(tr.Ng, d);
+  const float absDen = fabsf(den);
+  const float sgn = den < 0.0f ? -1.0f : 1.0f;
+  const float U = dot3(R, tr.e2) * sgn;
+  const float V = dot3(R, tr.e1) * sgn;
+  const float T = dot3(tr.Ng, C) * sgn;
+  if (!(den != 0.0f) || !(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= absDen) || !(T > 0.0f)) return false;
+  t = T / absDen; u = U / absDen; v = V / absDen;
+  return true;
+}
+
+// ------------------------------------------------------------------ BVH node (64 B): two child boxes + links
+// a = (lo0.x lo0.y lo0.z hi0.x)  b = (hi0.y hi0.z lo1.x lo1.y)  c = (lo1.z hi1.x hi1.y hi1.z)
+// d = (child0, child1, count0, count1); count>0 => child is the first sorted triangle of a leaf run
+struct BvhNode { float4 a, b, c; int4 d; };
+
+constexpr int kLeafMax = 4;      // a subtree with <= kLeafMax triangles is tested linearly
+constexpr int kStack = 64;       // >= depth of a 62-bit-key LBVH
+
+NLOS_HD float safe_rcp(float x) {
+  const float tiny = 1e-20f;
+  if (fabsf(x) < tiny) x = (f2i(x) < 0) ? -tiny : tiny;
+  return 1.0f / x;
+}
+
+struct Ray { f3 o, d, id, oid; };
+NLOS_HD Ray make_ray(f3 o, f3 d) {
+  Ray r; r.o = o; r.d = d; r.id = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  r.oid = mk3(o.x * r.id.x, o.y * r.id.y, o.z * r.id.z); return r;
+}
+// slab test against a (padded) box, clipped to [0, tlim]; returns entry distance
+NLOS_HD bool slab(const Ray& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tlim, float& tn) {
+  const float tx1 = fmaf(lox, r.id.x, -r.oid.x), tx2 = fmaf(hix, r.id.x, -r.oid.x);
+  const float ty1 = fmaf(loy, r.id.y, -r.oid.y), ty2 = fmaf(hiy, r.id.y, -r.oid.y);
+  const float tz1 = fmaf(loz, r.id.z, -r.oid.z), tz2 = fmaf(hiz, r.id.z, -r.oid.z);
+  const float tmn = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), 0.0f));
+  const float tmx = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), tlim));
+  tn = tmn;
+  return tmn <= tmx;
+}
+
+#if defined(__CUDA_ARCH__)
+#define NLOS_LDG4(p) __ldg(p)
+#else
+#define NLOS_LDG4(p) (*(p))
+#endif
+
+// does triangle j (sorted index) beat (t_self, prim_self) in the lexicographic nearest-hit order?
+NLOS_HD bool tri_occludes(const float4* __restrict__ ttris, int j, const Ray& r, float t_self, int prim_self) {
+  const float4 q0 = NLOS_LDG4(ttris + 4 * (size_t)j);
+  const int prim = f2i(q0.w);
+  if (prim == prim_self) return false;
+  const float4 q1 = NLOS_LDG4(ttris + 4 * (size_t)j + 1);
+  const float4 q2 = NLOS_LDG4(ttris + 4 * (size_t)j + 2);
+  const float4 q3 = NLOS_LDG4(ttris + 4 * (size_t)j + 3);
+  TriRec tr; tr.v0 = xyz(q0); tr.e1 = xyz(q1); tr.e2 = xyz(q2); tr.Ng = xyz(q3);
+  float t, u, v;
+  if (!isect(tr, r.o, r.d, t, u, v)) return false;
+  return t < t_self || (t == t_self && prim < prim_self);
+}
+
+// Any-hit query equivalent to "nearest hit (min t, ties -> lowest prim) is NOT prim_self".
+// num_internal = F-1 Karras nodes (root = 0); when the whole mesh is one leaf run, root_count = F.
+NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restrict__ ttris, int root_count,
+                      const Ray& r, float t_self, int prim_self, uint32_t* n_box = nullptr, uint32_t* n_tri = nullptr) {
+  if (root_count > 0) {
+    for (int j = 0; j < root_count; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, j, r, t_self, prim_self)) return true; }
+    return false;
+  }
+  const float tlim = t_self * 1.000001f;        // a tie on t must still be reachable
+  int stack[kStack]; int sp = 0; int node = 0;
+  while (true) {
+    const float4 a = NLOS_LDG4(&nodes[node].a), b = NLOS_LDG4(&nodes[node].b), c = NLOS_LDG4(&nodes[node].c);
+    const int4 d = *reinterpret_cast<const int4*>(&nodes[node].d);
+    float t0, t1;
+    bool h0 = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
+    bool h1 = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
+    if (n_box) *n_box += 2;
+    if (h0 && d.z > 0) { for (int j = 0; j < d.z; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, d.x + j, r, t_self, prim_self)) return true; } h0 = false; }
+    if (h1 && d.w > 0) { for (int j = 0; j < d.w; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, d.y + j, r, t_self, prim_self)) return true; } h1 = false; }
+    if (h0 && h1) {
+      const bool first0 = t0 <= t1;
+      stack[sp++] = first0 ? d.y : d.x; node = first0 ? d.x : d.y;
+    } else if (h0) node = d.x;
+    else if (h1) node = d.y;
+    else { if (sp == 0) return false; node = stack[--sp]; }
+  }
+}
+
+// ------------------------------------------------------------------ LBVH construction helpers (Karras 2012)
+NLOS_HD uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u; return v;
+}
+NLOS_HD uint32_t morton30(float x, float y, float z) {   // x,y,z in [0,1]
+  const float s = 1024.0f;
+  const uint32_t xi = (uint32_t)fminf(fmaxf(x * s, 0.0f), 1023.0f);
+  const uint32_t yi = (uint32_t)fminf(fmaxf(y * s, 0.0f), 1023.0f);
+  const uint32_t zi = (uint32_t)fminf(fmaxf(z * s, 0.0f), 1023.0f);
+  return (expand_bits10(xi) << 2) | (expand_bits10(yi) << 1) | expand_bits10(zi);
+}
+NLOS_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+// keys are unique (low 32 bits = triangle index), so delta is a plain common-prefix length
+NLOS_HD int lbvh_delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  return clz64(keys[i] ^ keys[j]);
+}
+// internal node i covers sorted leaves [first,last]; children split at 'split' | 'split+1'
+NLOS_HD void lbvh_range(const uint64_t* __restrict__ keys, int n, int i, int& first, int& last, int& split) {
+  const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t <= 1) break;
+  }
+  split = i + s * d + (d < 0 ? -1 : 0);
+  first = i < j ? i : j; last = i < j ? j : i;
+}
+
+// ------------------------------------------------------------------ GGX (confocal: wi = wo = h = w), x = n.w
+NLOS_HD float ggx_D(float a, float nw) {
+  if (nw <= 0) return 0.0f;
+  const float nw2 = nw * nw;
+  const float be = (1.0f - nw2) / (a * a) / nw2;
+  const float root = (1.0f + be) * nw2;
+  float result = 1.0f / ((float)M_PI * a * a * root * root);
+  if (result * nw < 1e-20f) result = 0;
+  return result;
+}
+NLOS_HD float ggx_G1(float a, float nw) {
+  if (nw <= 0) return 0.0f;
+  if (nw >= 1.0f) return 1.0f;
+  const float root = a * a + (1.0f - a * a) * nw * nw;
+  return 2.0f / (nw + sqrtf(root));
+}
+NLOS_HD float ggx_eval(float a, float nw) {
+  if (nw <= 0) return 0.0f;
+  const float Dv = ggx_D(a, nw); if (Dv == 0) return 0.0f;
+  const float g = ggx_G1(a, nw);
+  return Dv * (g * g) / 4.0f;
+}
+NLOS_HD float ggx_eval_adiff(float a, float nw) {
+  if (nw <= 0) return 0.0f;
+  const float Dv = ggx_D(a, nw); if (Dv == 0) return 0.0f;
+  const float g1 = ggx_G1(a, nw), Gv = g1 * g1;
+  const float nw2 = nw * nw, a2 = a * a;
+  const float val = a2 * nw2 - nw2 + 1;
+  const float Dp = -(2.0f * a * (a2 * nw2 + nw2 - 1)) / ((float)M_PI * val * val * val);
+  float g1p = 0.0f;
+  if (nw < 1.0f) { const float vv = sqrtf(a2 - nw2 * (a2 - 1)); const float root = nw + vv; g1p = 2.0f * a * (nw2 - 1.0f) / (vv * root * root); }
+  const float Gp = 2.0f * g1p * g1;
+  return (Dp * Gv + Gp * Dv) / 4.0f;
+}
+// d f / d (n.w); df/dn = S*w, df/dw = S*n
+NLOS_HD float ggx_eval_xdiff(float a, float nw) {
+  if (nw <= 0) return 0.0f;
+  const float Dv = ggx_D(a, nw); if (Dv == 0) return 0.0f;
+  const float g1 = ggx_G1(a, nw), Gv = g1 * g1;
+  const float nw2 = nw * nw, a2 = a * a;
+  const float root = (a2 - 1.0f) * nw2 + 1.0f;
+  const float Dp = -(4.0f * a2 * nw * (a2 - 1.0f)) / ((float)M_PI * root * root * root);
+  float g1p = 0.0f;
+  if (nw < 1.0f) { const float temp = sqrtf(a2 - nw2 * (a2 - 1.0f)); const float rt = nw + temp; g1p = -2.0f * (1.0f - (nw * (a2 - 1.0f)) / temp) / rt / rt; }
+  const float Gp = 2.0f * g1p * g1;
+  return (Dp * Gv + Gp * Dv) / 4.0f;
+}
+
+// ------------------------------------------------------------------ one stratified sample
+struct ShadeTri { f3 v1, v2, v3, nf; float A; int i1, i2, i3; };
+
+struct SampleGeom { f3 d; float u, v, w, r, t; };
+
+// generate the sample point / ray direction (TG.cpp:184-195) and run the self intersection that yields
+// the hit barycentrics the reference reads back from Embree (TG.cpp:208-212).
+NLOS_HD bool sample_self_hit(uint64_t seed, int64_t src_global, int prim, int k, f3 o, const ShadeTri& st, const TriRec& tr, SampleGeom& g) {
+  float S, T; sample_ST(seed, src_global, prim, k, S, T);
+  const float sqrtT = sqrtf(T);
+  const float u = 1 - sqrtT, v = (1 - S) * sqrtT, w = S * sqrtT;
+  const f3 point = blend3(u, st.v1, v, st.v2, w, st.v3);
+  const f3 q = point - o;
+  const float inv = 1.0f / len3(q);
+  g.d = q * inv;
+  float t, hu, hv;
+  if (!isect(tr, o, g.d, t, hu, hv)) return false;
+  g.t = t; g.v = hu; g.w = hv; g.u = 1.0f - hu - hv;
+  const f3 pt = blend3(g.u, st.v1, g.v, st.v2, g.w, st.v3);
+  g.r = len3(pt - o);
+  return true;
+}
+
+// tap -> coarse-bin grouping shared by the smoothed forward splat and the gradient (DESIGN.md "K-tap
+// restructuring"): tap i of a sample in fine bin m0 lands in coarse bin floor((m0 + i - 2rs)/r).
+// For coarse bin b the taps are i in [ilo, ihi) with:
+NLOS_HD void tap_span(int64_t m0, int b, int r, int half /*2rs*/, int K, int& ilo, int& ihi) {
+  int64_t lo = (int64_t)b * r - m0 + half, hi = lo + r;
+  ilo = lo < 0 ? 0 : (lo > K ? K : (int)lo);
+  ihi = hi < 0 ? 0 : (hi > K ? K : (int)hi);
+}
+NLOS_HD int64_t floordiv(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+}  // namespace nlos

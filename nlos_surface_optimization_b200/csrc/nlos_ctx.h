@@ -1,0 +1,58 @@
+// nlos_ctx.h — host-side context behind the opaque nlos_ctx handle of include/nlos_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <map>
+#include "nlos_device.cuh"
+
+namespace nlos {
+
+// grow-only device buffer; reused across calls so a steady-state iteration does no cudaMalloc
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  void* ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr; cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      cudaError_t e = cudaMalloc(&p, want);
+      if (e != cudaSuccess) { p = nullptr; throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); }
+      cap = want;
+    }
+    return p;
+  }
+  template <class T> T* as(size_t n) { return reinterpret_cast<T*>(ensure(n * sizeof(T))); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Timing { float build_ms = 0, forward_ms = 0, residual_ms = 0, gradient_ms = 0, total_ms = 0; };
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_copy = nullptr;
+  std::string last_error;
+  // options (nlos_ctx_set_*)
+  uint64_t seed = 5489;          // boost::mt19937 default = the reference's built-in seed (sampler.cpp:25)
+  int64_t src_offset = 0;        // global index of the first source of this call (sharded runs)
+  int64_t num_sources_global = 0;  // 0 => normalise the gradient by this call's L (reference behaviour)
+  int reuse_visibility = 1;      // gradient pass consumes the forward pass's visibility bits
+  int timing_enabled = 0;
+  int chunk_forward = 0;         // sources per blockIdx.y in the forward pass (0 = auto)
+  int chunk_gradient = 0;        // same for the gradient pass
+  Timing timing;
+  uint64_t launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
+  std::map<std::string, DevBuf> bufs;
+  DevBuf& buf(const char* name) { return bufs[name]; }
+  ~Ctx();
+};
+
+// lbvh.cu
+void build_scene(Ctx& cx, const float* d_verts, int V, const int* d_faces, int F, const float* d_origin, int64_t L,
+                 const float* d_vnormal, const float* d_valbedo, DeviceScene& out);
+
+}  // namespace nlos

@@ -1,0 +1,405 @@
+// render_kernels.cu — K1 (forward), K3 (residual), K4 (vertex gradient), K5 (scalar gradients),
+// K6 (per-triangle intensity) and the debug visibility kernel.
+//
+// Work mapping (DESIGN.md "Kernel mapping"): one THREAD owns one triangle (Morton order, so a warp is 32
+// spatially adjacent triangles) and loops over a chunk of relay-wall sources; blockIdx.y selects the chunk.
+//   * rays of a warp share their origin and hit a compact patch  -> coherent BVH traversal
+//   * triangle data stays in registers for the whole source loop -> no re-gather per (source,triangle) task
+//   * the vertex gradient of a triangle accumulates in 9 FP64 registers across the source loop and is
+//     flushed with 9 atomics per (triangle, chunk) instead of 9*K atomics per visible sample
+//   * visibility is an ANY-HIT query bounded by the self-hit distance (equivalent to the reference's
+//     "nearest hit == sampled triangle", TG.cpp:206) and is skipped for samples whose contribution is
+//     exactly zero (back-facing / out of range)
+//   * the forward pass leaves one visibility bit per sample (warp ballot) that the gradient pass reuses,
+//     so the gradient pass traces no rays (legitimate: both passes use identical samples)
+//
+// Reference: smoothed_transient/transient_and_gradient.cpp:122-237 (forward task), :843-1007 (gradient task),
+// :571-695 (albedo), :22-119 (intensity); ggx/transient_and_gradient.cpp:126-243, 385-512, 648-823.
+#include "nlos_ctx.h"
+#include "render_kernels.h"
+
+namespace nlos {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+struct TriRegs {
+  ShadeTri st; TriRec tr; int prim;
+  f3 n1, n2, n3; float a1, a2, a3;
+};
+
+template <bool HAS_VN, bool HAS_VA>
+__device__ __forceinline__ void load_tri(const DeviceScene& sc, int p, TriRegs& t) {
+  const float4 s0 = __ldg(sc.stris + 4 * (size_t)p), s1 = __ldg(sc.stris + 4 * (size_t)p + 1), s2 = __ldg(sc.stris + 4 * (size_t)p + 2), s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+  t.st.v1 = xyz(s0); t.st.A = s0.w; t.st.v2 = xyz(s1); t.st.v3 = xyz(s2); t.st.nf = mk3(s1.w, s2.w, s3.x);
+  t.st.i1 = __float_as_int(s3.y); t.st.i2 = __float_as_int(s3.z); t.st.i3 = __float_as_int(s3.w);
+  const float4 q0 = __ldg(sc.ttris + 4 * (size_t)p), q1 = __ldg(sc.ttris + 4 * (size_t)p + 1), q2 = __ldg(sc.ttris + 4 * (size_t)p + 2), q3 = __ldg(sc.ttris + 4 * (size_t)p + 3);
+  t.tr.v0 = xyz(q0); t.tr.e1 = xyz(q1); t.tr.e2 = xyz(q2); t.tr.Ng = xyz(q3); t.prim = __float_as_int(q0.w);
+  if (HAS_VN) {
+    const float* vn = sc.vnormal;
+    t.n1 = mk3(__ldg(vn + 3 * (size_t)t.st.i1), __ldg(vn + 3 * (size_t)t.st.i1 + 1), __ldg(vn + 3 * (size_t)t.st.i1 + 2));
+    t.n2 = mk3(__ldg(vn + 3 * (size_t)t.st.i2), __ldg(vn + 3 * (size_t)t.st.i2 + 1), __ldg(vn + 3 * (size_t)t.st.i2 + 2));
+    t.n3 = mk3(__ldg(vn + 3 * (size_t)t.st.i3), __ldg(vn + 3 * (size_t)t.st.i3 + 1), __ldg(vn + 3 * (size_t)t.st.i3 + 2));
+  }
+  if (HAS_VA) { t.a1 = __ldg(sc.valbedo + t.st.i1); t.a2 = __ldg(sc.valbedo + t.st.i2); t.a3 = __ldg(sc.valbedo + t.st.i3); }
+}
+
+template <bool HAS_VN>
+__device__ __forceinline__ f3 shading_normal(const TriRegs& t, const SampleGeom& g) { return HAS_VN ? blend3(g.u, t.n1, g.v, t.n2, g.w, t.n3) : t.st.nf; }
+template <bool HAS_VA>
+__device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGeom& g) { return HAS_VA ? blend1(g.u, t.a1, g.v, t.a2, g.w, t.a3) : 1.0f; }
+
+// ---------------------------------------------------------------------------------------------- K1 forward
+// MODE 0: transient histogram (+ optional visibility bits);  MODE 1: per-triangle intensity (K6)
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
+__global__ void __launch_bounds__(kBlock) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
+                                                    uint32_t* __restrict__ vis, const double* __restrict__ wprefix) {
+  extern __shared__ double s_w[];           // SMOOTH: prefix sums of the Gaussian taps, K+1 entries
+  if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += blockDim.x) s_w[i] = wprefix[i]; __syncthreads(); }
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < sc.F;
+  TriRegs t;
+  if (active) load_tri<HAS_VN, HAS_VA>(sc, p, t);
+  const int64_t s0 = (int64_t)blockIdx.y * P.chunk;
+  const int64_t s1 = s0 + P.chunk < P.L ? s0 + P.chunk : P.L;
+  const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
+  const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = p >> 5;
+  double acc = 0.0;                         // MODE 1
+  for (int64_t s = s0; s < s1; ++s) {
+    const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
+    const f3 o = xyz(o4), on = xyz(n4);
+    for (int k = 0; k < P.spp; ++k) {
+      bool bit = false;
+      SampleGeom g;
+      if (active && sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
+        const f3 n = shading_normal<HAS_VN>(t, g);
+        float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;        // TG.cpp:224-227
+        if (ff > 0.0f) {                                              // max(0,ff)==0 adds exactly 0 (TG.cpp:228)
+          const Ray ray = make_ray(o, g.d);
+          if (!occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim)) {
+            bit = true;
+            const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
+            float val = t.st.A * alb * ff * ff;
+            if (GGX) val = val * ggx_eval(P.alpha, dot3(n, -g.d));    // ggx/TG.cpp:236-238
+            const double dv = (double)val / (double)P.spp;
+            if (MODE == 1) acc += dv;
+            else {
+              const int64_t bin = (int64_t)floorf((2.0f * g.r - P.lb) / P.res_fwd);   // TG.cpp:229
+              if (bin >= 0 && bin < nbf) {
+                if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
+                else {
+                  const int half = 2 * P.r_fwd * P.s_bin;
+                  int64_t b0 = floordiv(bin - half, P.r_fwd), b1 = floordiv(bin + half, P.r_fwd);
+                  if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+                  for (int64_t b = b0; b <= b1; ++b) {
+                    int ilo, ihi; tap_span(bin, (int)b, P.r_fwd, half, P.K, ilo, ihi);
+                    const double wsum = s_w[ihi] - s_w[ilo];
+                    if (ihi > ilo) atomicAdd(out + s * P.numBins + b, dv * wsum);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if (WRITE_VIS) {
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) vis[((size_t)s * P.spp + k) * P.words_per_row + warp_global] = m;
+      }
+    }
+  }
+  if (MODE == 1 && active && acc != 0.0) atomicAdd(out + t.prim, acc);
+}
+
+// ---------------------------------------------------------------------------------------------- K3 residual
+// diff = (data - T) [-> 2 d^3 if loss_flag] * weight      (SSG.cpp:543-550)
+__global__ void k_residual(const double* __restrict__ data, const double* __restrict__ weight, const double* __restrict__ T, double* __restrict__ diff, size_t n, int loss_flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double d = data[i] - T[i];
+    if (loss_flag == 1) d = 2 * d * d * d;
+    diff[i] = d * weight[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K4/K5 gradients
+// KIND 0: vertex gradient (9 FP64 register accumulators per thread), 1: albedo scalar, 2: GGX alpha scalar
+template <bool GGX, bool HAS_VN, bool HAS_VA, int KIND, bool USE_VIS>
+__global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
+                                                     const uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
+                                                     const double* __restrict__ dprefix, double* __restrict__ out) {
+  extern __shared__ double s_tab[];         // [0..K] prefix of w_i, [K+1..2K+1] prefix of w_i*delta_i
+  double* s_w = s_tab; double* s_d = s_tab + (P.K + 1);
+  for (int i = threadIdx.x; i <= P.K; i += blockDim.x) { s_w[i] = wprefix[i]; s_d[i] = dprefix[i]; }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < sc.F;
+  TriRegs t;
+  if (active) load_tri<HAS_VN, HAS_VA>(sc, p, t);
+  const int64_t s0 = (int64_t)blockIdx.y * P.chunk;
+  const int64_t s1 = s0 + P.chunk < P.L ? s0 + P.chunk : P.L;
+  const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = p >> 5;
+  const int half = 2 * P.r_grad * P.s_bin;
+  double g1x = 0, g1y = 0, g1z = 0, g2x = 0, g2y = 0, g2z = 0, g3x = 0, g3y = 0, g3z = 0, gs = 0;
+  f3 e1, e2, e3;
+  if (active) { e1 = t.st.v3 - t.st.v2; e2 = t.st.v1 - t.st.v3; e3 = t.st.v2 - t.st.v1; }
+  for (int64_t s = s0; s < s1; ++s) {
+    const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
+    const f3 o = xyz(o4), on = xyz(n4);
+    for (int k = 0; k < P.spp; ++k) {
+      bool bit = active;
+      if (USE_VIS) {
+        const unsigned m = __ldg(vis + ((size_t)s * P.spp + k) * P.words_per_row + warp_global);
+        bit = active && ((m >> lane) & 1u);
+      }
+      if (!bit) continue;
+      SampleGeom g;
+      if (!sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) continue;
+      if (!(g.r <= ub_half && g.r >= lb_half)) continue;
+      const f3 n = shading_normal<HAS_VN>(t, g);
+      const f3 d = g.d; const float hl = g.r;
+      float c2 = dot3(on, d), c3 = dot3(n, -d);                       // TG.cpp:944-947
+      if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+      if (!(c2 * c3 > 0.0f)) continue;                                // every term below carries c2*c3
+      if (!USE_VIS) { const Ray ray = make_ray(o, d); if (occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim)) continue; }
+      const float alb = shading_albedo<HAS_VA>(t, g);
+      const float ff = c2 * c3 / hl / hl;
+      // K-tap sums against the residual row, grouped per coarse bin (DESIGN.md "K-tap restructuring")
+      const double x = ((double)(2.0f * hl) - (double)P.lb) * P.inv_res_fine;
+      const int64_t m0 = (int64_t)floor(x);
+      int64_t b0 = floordiv(m0 - half, P.r_grad), b1 = floordiv(m0 + half, P.r_grad);
+      if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+      double At = 0.0, Bt = 0.0;
+      const double* drow = diff + s * P.numBins;
+      for (int64_t b = b0; b <= b1; ++b) {
+        int ilo, ihi; tap_span(m0, (int)b, P.r_grad, half, P.K, ilo, ihi);
+        const double df = __ldg(drow + b);
+        At += (s_w[ihi] - s_w[ilo]) * df;
+        Bt += (s_d[ihi] - s_d[ilo]) * df;
+      }
+      At *= -2.0; Bt *= -2.0;
+      if (KIND == 1) {                                                // TG.cpp:677-688
+        const double g0 = (double)(ff * ff);
+        gs += (double)t.st.A * (g0 * At) / (double)P.spp;
+      } else if (KIND == 2) {                                         // ggx/TG.cpp:492-505
+        const double g0 = (double)(alb * ff * ff * ggx_eval_adiff(P.alpha, dot3(n, -d)));
+        gs += (double)t.st.A * g0 * At / (double)P.spp;
+      } else {
+        const float hl2 = hl * hl, hl4 = hl2 * hl2, hl5 = hl4 * hl;
+        f3 t1, gn = mk3(0.f, 0.f, 0.f); float inten;
+        if (!GGX) {
+          inten = alb * ff * ff;                                      // TG.cpp:950
+          t1 = (2 * alb * c2 * c3) * (on * c3 - n * c2 + (4 * (-d)) * c2 * c3);   // :953
+          t1 = t1 / hl5;                                              // :954
+          if (HAS_VN && P.testing_flag == 0) {                        // :959-964
+            gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / hl4;
+            const float ct = dot3(gn, n); gn = gn - n * ct;
+          }
+        } else {                                                      // ggx/TG.cpp:756-780
+          const float nw = dot3(n, -d);
+          const float brdf = ggx_eval(P.alpha, nw);
+          const float S = ggx_eval_xdiff(P.alpha, nw);
+          const f3 dn = S * (-d), dw = S * n;
+          const f3 dx = -dw + d * dot3(d, dw) / hl;                   // :759 (sic)
+          inten = alb * ff * ff * brdf;
+          f3 t11 = (2 * c2 * c3) * (on * c3 - n * c2 + (4 * (-d)) * c2 * c3);
+          t11 = t11 / hl5; t11 = t11 * brdf;
+          t1 = t11 + (ff * ff) * dx;
+          if (HAS_VN && P.testing_flag == 0) {
+            gn = (-2 * d) * c3 * c2 * c2 * brdf; gn = gn / hl4;
+            gn = gn + (ff * ff) * dn;
+            const float ct = dot3(gn, n); gn = gn - n * ct;
+          }
+        }
+        f3 t2 = n * inten;                                            // :956
+        t2 = (t2 + gn) / (2 * t.st.A);                                // :966
+        // sum_i g_k(i) = (t1 b_k + t2 x e_k) At + (2 I / sigma^2) d b_k Bt
+        const float fa = (float)At;
+        const float fb = (float)((double)inten * P.two_over_sigma2 * Bt);
+        const float sA = t.st.A;
+        const double inv_spp = 1.0 / (double)P.spp;
+        f3 gk;
+        gk = (t1 * g.u + cross3(t2, e1)) * fa + d * (g.u * fb);
+        g1x += (double)(sA * gk.x) * inv_spp; g1y += (double)(sA * gk.y) * inv_spp; g1z += (double)(sA * gk.z) * inv_spp;
+        gk = (t1 * g.v + cross3(t2, e2)) * fa + d * (g.v * fb);
+        g2x += (double)(sA * gk.x) * inv_spp; g2y += (double)(sA * gk.y) * inv_spp; g2z += (double)(sA * gk.z) * inv_spp;
+        gk = (t1 * g.w + cross3(t2, e3)) * fa + d * (g.w * fb);
+        g3x += (double)(sA * gk.x) * inv_spp; g3y += (double)(sA * gk.y) * inv_spp; g3z += (double)(sA * gk.z) * inv_spp;
+      }
+    }
+  }
+  if (KIND == 0) {
+    if (active) {
+      if (g1x != 0.0 || g1y != 0.0 || g1z != 0.0) { atomicAdd(out + 3 * (size_t)t.st.i1, g1x); atomicAdd(out + 3 * (size_t)t.st.i1 + 1, g1y); atomicAdd(out + 3 * (size_t)t.st.i1 + 2, g1z); }
+      if (g2x != 0.0 || g2y != 0.0 || g2z != 0.0) { atomicAdd(out + 3 * (size_t)t.st.i2, g2x); atomicAdd(out + 3 * (size_t)t.st.i2 + 1, g2y); atomicAdd(out + 3 * (size_t)t.st.i2 + 2, g2z); }
+      if (g3x != 0.0 || g3y != 0.0 || g3z != 0.0) { atomicAdd(out + 3 * (size_t)t.st.i3, g3x); atomicAdd(out + 3 * (size_t)t.st.i3 + 1, g3y); atomicAdd(out + 3 * (size_t)t.st.i3 + 2, g3z); }
+    }
+  } else {
+    // block reduction of the scalar, one atomic per block
+    __shared__ double s_red[kBlock / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    if (lane == 0) s_red[threadIdx.x >> 5] = gs;
+    __syncthreads();
+    if (threadIdx.x == 0) { double tot = 0; for (int w = 0; w < kBlock / 32; ++w) tot += s_red[w]; if (tot != 0.0) atomicAdd(out, tot); }
+  }
+}
+
+// gradient[d] += acc[d] / L        (TG.cpp:561-565: '+=' into the caller's array)
+__global__ void k_finalize_gradient(const double* __restrict__ acc, double* __restrict__ gradient, size_t n, double inv_L) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) gradient[i] += acc[i] * inv_L;
+}
+
+// ---------------------------------------------------------------------------------------------- debug visibility
+// Pure geometry: bit = (nearest hit == sampled triangle), no shading-based skipping. vis_out[L,F,spp] in caller order.
+__global__ void __launch_bounds__(kBlock) k_visibility(const DeviceScene sc, const RenderParams P, uint8_t* __restrict__ vis_out, unsigned long long* __restrict__ counters) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= sc.F) return;
+  TriRegs t; load_tri<false, false>(sc, p, t);
+  const int64_t s0 = (int64_t)blockIdx.y * P.chunk;
+  const int64_t s1 = s0 + P.chunk < P.L ? s0 + P.chunk : P.L;
+  unsigned long long nb = 0, nt = 0, nr = 0;
+  for (int64_t s = s0; s < s1; ++s) {
+    const f3 o = xyz(__ldg(P.origin + s));
+    for (int k = 0; k < P.spp; ++k) {
+      SampleGeom g; uint8_t bit = 0;
+      if (sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) {
+        const Ray ray = make_ray(o, g.d);
+        uint32_t cb = 0, ct = 0;
+        bit = occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim, &cb, &ct) ? 0 : 1;
+        nb += cb; nt += ct; nr += 1;
+      }
+      vis_out[((size_t)s * sc.F + t.prim) * P.spp + k] = bit;
+    }
+  }
+  if (counters) { atomicAdd(counters, nr); atomicAdd(counters + 1, nb); atomicAdd(counters + 2, nt); }
+}
+
+__global__ void k_pack4(const float* __restrict__ in, float4* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.f);
+}
+__global__ void k_pathlengths(double* __restrict__ pl, int B, float lb, float res) {   // SST.cpp:126-129
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) pl[i] = (double)(lb + i * res);
+}
+
+inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
+  return dim3((unsigned)((sc.F + kBlock - 1) / kBlock), (unsigned)((P.L + P.chunk - 1) / P.chunk), 1);
+}
+
+template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
+void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+  const dim3 grid = sample_grid(sc, P);
+  const size_t smem = SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0;
+  if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
+  else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
+  cx.launches += 1;
+}
+
+template <bool GGX, bool VN, bool VA, int KIND>
+void launch_gradient_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, const double* diff, const uint32_t* vis,
+                       const double* wprefix, const double* dprefix, double* out) {
+  const dim3 grid = sample_grid(sc, P);
+  const size_t smem = 2 * (size_t)(P.K + 1) * sizeof(double);
+  if (vis) k_gradient<GGX, VN, VA, KIND, true><<<grid, kBlock, smem, cx.stream>>>(sc, P, diff, vis, wprefix, dprefix, out);
+  else k_gradient<GGX, VN, VA, KIND, false><<<grid, kBlock, smem, cx.stream>>>(sc, P, diff, vis, wprefix, dprefix, out);
+  cx.launches += 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers
+void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* transient, uint32_t* vis, const double* wprefix) {
+  if (sc.F <= 0 || P.L <= 0) return;
+  const bool vn = sc.vnormal != nullptr, va = sc.valbedo != nullptr, sm = P.r_fwd > 1;
+#define NLOS_FWD(G, N, A, S) launch_forward_t<G, N, A, S, 0>(cx, sc, P, transient, vis, wprefix)
+  if (!ggx) {
+    if (!vn && !va) { if (sm) NLOS_FWD(false, false, false, true); else NLOS_FWD(false, false, false, false); }
+    else if (vn && !va) { if (sm) NLOS_FWD(false, true, false, true); else NLOS_FWD(false, true, false, false); }
+    else if (!vn && va) { if (sm) NLOS_FWD(false, false, true, true); else NLOS_FWD(false, false, true, false); }
+    else { if (sm) NLOS_FWD(false, true, true, true); else NLOS_FWD(false, true, true, false); }
+  } else {
+    if (!vn && !va) { if (sm) NLOS_FWD(true, false, false, true); else NLOS_FWD(true, false, false, false); }
+    else if (vn && !va) { if (sm) NLOS_FWD(true, true, false, true); else NLOS_FWD(true, true, false, false); }
+    else if (!vn && va) { if (sm) NLOS_FWD(true, false, true, true); else NLOS_FWD(true, false, true, false); }
+    else { if (sm) NLOS_FWD(true, true, true, true); else NLOS_FWD(true, true, true, false); }
+  }
+#undef NLOS_FWD
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity) {
+  if (sc.F <= 0 || P.L <= 0) return;
+  const bool vn = sc.vnormal != nullptr;
+  if (!ggx) { if (vn) launch_forward_t<false, true, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); else launch_forward_t<false, false, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); }
+  else { if (vn) launch_forward_t<true, true, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); else launch_forward_t<true, false, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); }
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_residual(Ctx& cx, const double* data, const double* weight, const double* T, double* diff, size_t n, int loss_flag) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  k_residual<<<blocks, 256, 0, cx.stream>>>(data, weight, T, diff, n, loss_flag);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, int kind, const double* diff, const uint32_t* vis,
+                     const double* wprefix, const double* dprefix, double* out) {
+  if (sc.F <= 0 || P.L <= 0) return;
+  const bool vn = sc.vnormal != nullptr, va = sc.valbedo != nullptr;
+#define NLOS_GRAD(G, N, A, KD) launch_gradient_t<G, N, A, KD>(cx, sc, P, diff, vis, wprefix, dprefix, out)
+  if (kind == 0) {
+    if (!ggx) {
+      if (!vn && !va) NLOS_GRAD(false, false, false, 0); else if (vn && !va) NLOS_GRAD(false, true, false, 0);
+      else if (!vn && va) NLOS_GRAD(false, false, true, 0); else NLOS_GRAD(false, true, true, 0);
+    } else {
+      if (!vn && !va) NLOS_GRAD(true, false, false, 0); else if (vn && !va) NLOS_GRAD(true, true, false, 0);
+      else if (!vn && va) NLOS_GRAD(true, false, true, 0); else NLOS_GRAD(true, true, true, 0);
+    }
+  } else if (kind == 1) {
+    if (!vn && !va) NLOS_GRAD(false, false, false, 1); else if (vn && !va) NLOS_GRAD(false, true, false, 1);
+    else if (!vn && va) NLOS_GRAD(false, false, true, 1); else NLOS_GRAD(false, true, true, 1);
+  } else {
+    if (!vn && !va) NLOS_GRAD(true, false, false, 2); else if (vn && !va) NLOS_GRAD(true, true, false, 2);
+    else if (!vn && va) NLOS_GRAD(true, false, true, 2); else NLOS_GRAD(true, true, true, 2);
+  }
+#undef NLOS_GRAD
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_finalize_gradient(Ctx& cx, const double* acc, double* gradient, size_t n, double inv_L) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  k_finalize_gradient<<<blocks, 256, 0, cx.stream>>>(acc, gradient, n, inv_L);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_visibility(Ctx& cx, const DeviceScene& sc, const RenderParams& P, uint8_t* vis_out, unsigned long long* counters) {
+  if (sc.F <= 0 || P.L <= 0) return;
+  k_visibility<<<sample_grid(sc, P), kBlock, 0, cx.stream>>>(sc, P, vis_out, counters);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n) {
+  if (n == 0) return;
+  k_pack4<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, cx.stream>>>(in, out, n);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res) {
+  if (B <= 0) return;
+  k_pathlengths<<<(B + 255) / 256, 256, 0, cx.stream>>>(pl, B, lb, res);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace nlos

@@ -1,0 +1,17 @@
+// render_kernels.h — host-callable launchers of render_kernels.cu (all asynchronous on cx.stream).
+#pragma once
+#include "nlos_ctx.h"
+
+namespace nlos {
+
+void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* transient, uint32_t* vis, const double* wprefix);
+void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity);
+void launch_residual(Ctx& cx, const double* data, const double* weight, const double* T, double* diff, size_t n, int loss_flag);
+void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, int kind, const double* diff, const uint32_t* vis,
+                     const double* wprefix, const double* dprefix, double* out);
+void launch_finalize_gradient(Ctx& cx, const double* acc, double* gradient, size_t n, double inv_L);
+void launch_visibility(Ctx& cx, const DeviceScene& sc, const RenderParams& P, uint8_t* vis_out, unsigned long long* counters);
+void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n);
+void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res);
+
+}  // namespace nlos

@@ -1,0 +1,254 @@
+"""GPU parity: the sm_100a path (through the C ABI / reference-signature modules) against the CPU oracle on
+identical fixed-seed samples.  Bars (BASELINE.json north_star): per-sample visibility bit-exact, transient
+relative L2 <= 1e-5, gradients relative L2 <= 1e-4."""
+import numpy as np
+import pytest
+from helpers import LB, UB, RES, TOL_TRANSIENT, TOL_GRADIENT, rel_l2, make_target
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(name):
+    from nlos_surface_optimization_b200 import scenes
+    if name == 'fan8':
+        v, f = scenes.fan8(); o, n = scenes.wall_grid(4); ns = 8 * 64
+    elif name == 'occluders':
+        v, f = scenes.merge([scenes.quad(0.40, 0.08), scenes.quad(0.55, 0.2), scenes.icosphere(2, 0.05, (0.1, -0.05, 0.3))])
+        o, n = scenes.wall_grid(5); ns = f.shape[0] * 8
+    elif name == 'ico':
+        v, f = scenes.icosphere(4, 0.1, (0.02, -0.03, 0.45), noise=0.03, seed=3); o, n = scenes.wall_grid(6); ns = 20000
+    elif name == 'bunny':
+        v, f = scenes.bunny(); o, n = scenes.wall_grid(4); ns = 20000
+    else:
+        raise KeyError(name)
+    return o, n, v, f, ns
+
+
+@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny'])
+def test_visibility_bit_exact(name, oracle, gpu_ctx):
+    import nlos_surface_optimization_b200 as nb
+    o, n, v, f, ns = _scene(name)
+    ref = oracle.transient(o, n, v, f, ns, LB, UB, RES, want_visibility=True)[2]
+    vis, cnt = nb.debug_visibility(o, v, f, ns, ctx=gpu_ctx)
+    assert vis.shape == ref.shape
+    assert np.array_equal(vis, ref), 'visibility differs in %d of %d samples' % (int((vis != ref).sum()), ref.size)
+    assert cnt['rays'] > 0
+
+
+@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny'])
+@pytest.mark.parametrize('refine,sigma', [(1, 1), (10, 1)])
+def test_forward_transient(name, refine, sigma, oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene(name)
+    T_ref, pl_ref = oracle.transient(o, n, v, f, ns, LB, UB, RES, refine, sigma)[:2]
+    B = T_ref.shape[1]
+    T = np.full((o.shape[0], B), 7.0); pl = np.zeros(B)     # callee must zero the transient (TG.cpp:291)
+    renderer.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, T, pl, refine, sigma, ctx=gpu_ctx)
+    assert np.array_equal(pl, pl_ref)
+    assert T_ref.sum() > 0
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    if refine == 1:
+        # unsmoothed histogram: identical set of non-empty bins
+        assert np.array_equal(T > 0, T_ref > 0)
+
+
+@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny'])
+def test_vertex_gradient(name, oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene(name)
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    T_ref, G_ref, pl_ref = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, testing_flag=1, loss_flag=0)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert np.linalg.norm(G_ref) > 0
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+    # '+=' semantics (TG.cpp:563): a second call accumulates
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(G, 2 * G_ref) <= TOL_GRADIENT
+
+
+def test_gradient_without_visibility_reuse(oracle, gpu_ctx):
+    """The gradient pass re-tracing its rays gives the same result as consuming the forward pass's bits."""
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene('ico')
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    B = data.shape[1]
+    out = []
+    for reuse in (1, 0):
+        gpu_ctx.set_option('reuse_visibility', reuse)
+        T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+        renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+        out.append(G)
+    gpu_ctx.set_option('reuse_visibility', 1)
+    assert rel_l2(out[1], out[0]) <= 1e-12
+
+
+@pytest.mark.parametrize('loss_flag,sigma', [(1, 1), (0, 5)])
+def test_vertex_gradient_variants(loss_flag, sigma, oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene('ico')
+    refine = 4
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    weight = np.ascontiguousarray(weight * np.linspace(0.5, 1.5, weight.shape[1])[None, :])
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, refine, sigma, testing_flag=1, loss_flag=loss_flag)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, refine, sigma, 1, loss_flag, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+
+
+@pytest.mark.parametrize('testing_flag', [0, 1])
+def test_shading_gradient(testing_flag, oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer, scenes
+    o, n, v, f, ns = _scene('ico')
+    vn = scenes.vertex_normals(v, f)
+    data, weight = make_target(oracle, o, n, v, f, ns, vertex_normal=vn)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, testing_flag=testing_flag, vertex_normal=vn)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedShadingGradient(o, n, v, f, vn, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, testing_flag, 0, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+    T2 = np.zeros_like(T)
+    renderer.renderStreamedTransientShading(o, n, v, vn, f, ns, LB, UB, RES, T2, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(T2, T_ref) <= TOL_TRANSIENT
+
+
+def test_albedo_paths(oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene('ico')
+    rng = np.random.RandomState(0)
+    alb = np.ascontiguousarray(0.5 + rng.rand(v.shape[0]), dtype=np.float32)
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, vertex_albedo=alb)
+    _, g_ref = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, vertex_albedo=alb, kind=1)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradientWithAlbedo(o, n, v, f, alb, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+    T3 = np.zeros_like(T)
+    g = renderer.renderStreamedGradientAlbedo(o, n, v, f, alb, ns, LB, UB, RES, T3, pl, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T3, T_ref) <= TOL_TRANSIENT
+    assert abs(g - g_ref) <= TOL_GRADIENT * abs(g_ref)
+    T4 = np.zeros_like(T)
+    renderer.renderStreamedTransientwAlbedo(o, n, v, alb, f, ns, LB, UB, RES, T4, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(T4, T_ref) <= TOL_TRANSIENT
+
+
+def test_intensity(oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer, ggx
+    o, n, v, f, ns = _scene('ico')
+    I_ref = oracle.intensity(o, n, v, f, ns, LB, UB)
+    I = np.zeros(f.shape[0])
+    renderer.renderStreamedTriangleIntensity(o, n, v, f, ns, LB, UB, I, ctx=gpu_ctx)
+    assert rel_l2(I, I_ref) <= TOL_TRANSIENT
+    assert np.array_equal(I > 0, I_ref > 0)          # removeTriangle thresholds at 0 (exp_bunny/rendering.py:275-276)
+    Ig_ref = oracle.intensity(o, n, v, f, ns, LB, UB, alpha=0.3)
+    Ig = np.zeros(f.shape[0])
+    ggx.renderStreamedTriangleIntensity(o, n, v, f, 0.3, ns, LB, UB, Ig, ctx=gpu_ctx)
+    assert rel_l2(Ig, Ig_ref) <= TOL_TRANSIENT
+
+
+@pytest.mark.parametrize('alpha', [0.1, 0.5])
+def test_ggx(alpha, oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import ggx, scenes
+    o, n, v, f, ns = _scene('ico')
+    vn = scenes.vertex_normals(v, f)
+    data = oracle.transient(o, n, v, f, ns, LB, UB, RES, alpha=alpha * 2)[0]
+    weight = np.ones_like(data)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, testing_flag=1, alpha=alpha)
+    _, ga_ref = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, alpha=alpha, kind=2)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    ggx.renderStreamedGradient(o, n, v, f, alpha, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+    T2 = np.zeros_like(T)
+    ga = ggx.renderStreamedGradientAlpha(o, n, v, f, alpha, ns, LB, UB, RES, T2, pl, data, weight, 10, 1, ctx=gpu_ctx)
+    assert abs(ga - ga_ref) <= TOL_GRADIENT * abs(ga_ref)
+    # shading normals with the normal-variation term (testing_flag = 0)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, testing_flag=0, alpha=alpha, vertex_normal=vn)
+    G = np.zeros((v.shape[0], 3))
+    ggx.renderStreamedShadingGradient(o, n, v, f, vn, alpha, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+    assert rel_l2(G, G_ref) <= TOL_GRADIENT
+    T3 = np.zeros_like(T)
+    ggx.renderStreamedTransient(o, n, v, f, alpha, ns, LB, UB, RES, T3, pl, 10, 1, ctx=gpu_ctx)
+    T3_ref = oracle.transient(o, n, v, f, ns, LB, UB, RES, 10, 1, alpha=alpha)[0]
+    assert rel_l2(T3, T3_ref) <= TOL_TRANSIENT
+
+
+def test_device_tensors_in_place(oracle, gpu_ctx):
+    """torch CUDA tensors are used in place (no host staging) and give the same numbers as host arrays."""
+    import torch
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene('ico')
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    B = data.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    dev = torch.device('cuda:0')
+    to = lambda a: torch.from_numpy(a).to(dev)
+    dT = torch.zeros((o.shape[0], B), dtype=torch.float64, device=dev); dpl = torch.zeros(B, dtype=torch.float64, device=dev)
+    dG = torch.zeros((v.shape[0], 3), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    renderer.renderStreamedGradient(to(o), to(n), to(v), to(f), ns, LB, UB, RES, dT, dpl, dG, to(data), to(weight), 10, 1, 1, 0, ctx=gpu_ctx)
+    gpu_ctx.synchronize()
+    assert rel_l2(dT.cpu().numpy(), T) <= 1e-12
+    assert rel_l2(dG.cpu().numpy(), G) <= 1e-9
+
+
+def test_sharded_sources_match_single_call(oracle, gpu_ctx):
+    """Two half-slices of the wall with set_source_window reproduce the single-call result (multi-GPU contract)."""
+    from nlos_surface_optimization_b200 import renderer
+    o, n, v, f, ns = _scene('ico')
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    L, B = data.shape
+    T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    Ts = np.zeros((L, B)); Gs = np.zeros((v.shape[0], 3)); h = L // 2
+    try:
+        for a, b in ((0, h), (h, L)):
+            gpu_ctx.set_source_window(a, L)
+            Tpart = np.zeros((b - a, B))
+            renderer.renderStreamedGradient(np.ascontiguousarray(o[a:b]), np.ascontiguousarray(n[a:b]), v, f, ns, LB, UB, RES, Tpart, pl, Gs,
+                                            np.ascontiguousarray(data[a:b]), np.ascontiguousarray(weight[a:b]), 10, 1, 1, 0, ctx=gpu_ctx)
+            Ts[a:b] = Tpart
+    finally:
+        gpu_ctx.set_source_window(0, 0)
+    assert rel_l2(Ts, T) <= 1e-12
+    assert rel_l2(Gs, G) <= 1e-9
+
+
+def test_edge_cases(gpu_ctx):
+    import nlos_surface_optimization_b200 as nb
+    from nlos_surface_optimization_b200 import renderer, scenes
+    o, n = scenes.wall_grid(2)
+    v, f = scenes.quad(0.4, 0.1)
+    B = 1200
+    T = np.zeros((4, B)); pl = np.zeros(B)
+    # back-facing quad renders all-zero under the product clamp
+    renderer.renderStreamedTransient(o, n, v, np.ascontiguousarray(f[:, ::-1]), 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert T.sum() == 0
+    # single triangle (no BVH nodes), and a degenerate triangle in the mesh
+    f1 = np.ascontiguousarray(f[:1])
+    renderer.renderStreamedTransient(o, n, v, f1, 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert T.sum() > 0
+    fd = np.ascontiguousarray(np.vstack([f, [[0, 0, 1]]]).astype(np.int32))
+    renderer.renderStreamedTransient(o, n, v, fd, 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert np.isfinite(T).all() and T.sum() > 0
+    # shape errors are AssertionErrors like the Cython asserts (renderer.pyx:95-110)
+    with pytest.raises(AssertionError):
+        renderer.renderStreamedTransient(o, n, v, f, 64, LB, UB, RES, np.zeros((4, B - 1)), pl, 1, 1, ctx=gpu_ctx)
+    with pytest.raises(ValueError):
+        renderer.renderStreamedTransient(o.astype(np.float64), n, v, f, 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    # range window that excludes the mesh -> zeros
+    from nlos_surface_optimization_b200._arrays import num_bins
+    B2 = num_bins(0.0, 0.12, RES)
+    T2 = np.zeros((4, B2)); pl2 = np.zeros(B2)
+    renderer.renderStreamedTransient(o, n, v, f, 64, 0.0, 0.12, RES, T2, pl2, 1, 1, ctx=gpu_ctx)
+    assert T2.sum() == 0
