@@ -1,0 +1,140 @@
+"""Facade with the names and return values of the reference's exp_bunny/rendering.py:219-308 — the thin
+callers of the renderer boundary that every optimisation loop uses (exp_bunny/test.py:161-170).
+
+Only the functions ON the hot path are mirrored; remeshing / projection helpers of the reference file
+(:32-206, CGAL / El Topo / Embree-intersector / pyigl) stay in the reference and are untouched.  `mesh` and
+`opt` are the reference's ad-hoc objects (attributes v, f, vn, alpha, albedo, f_affinity / lighting,
+lighting_normal, sample_num, max_distance_bin, distance_resolution, bin_refine_resolution, sigma_bin,
+testing_flag, loss_flag, alpha_flag, albedo_flag, jitter, normal).
+"""
+import numpy as np
+
+from . import renderer, ggx
+
+
+def _bounds(opt):
+    return 0, opt.max_distance_bin * opt.distance_resolution, opt.distance_resolution
+
+
+def create_weighting_function(data, gamma=1):
+    """exp_bunny/rendering.py:208-217 (pure NumPy)."""
+    eps = 0.1
+    i_max = np.max(data)
+    normalized_data = data / i_max
+    weight = (normalized_data + eps) ** gamma
+    total = np.sum(weight)
+    weight = weight / total
+    weight *= data.shape[0] * data.shape[1]
+    return weight
+
+
+def _per_vertex_normal(mesh):
+    vn = np.empty(mesh.v.shape, dtype=np.float32, order='C')
+    try:
+        import cgal_api                                   # the reference's CGAL wrapper, if the user has it
+        cgal_api.per_vertex_normal(mesh.v, mesh.f, vn)
+    except ImportError:
+        from .scenes import vertex_normals                # host stand-in (area-weighted), CGAL is out of scope
+        vn[:] = vertex_normals(mesh.v, mesh.f)
+    return vn
+
+
+def inverseShadingRendering(mesh, data, weight, opt):
+    """:219-229"""
+    mesh.vn = _per_vertex_normal(mesh)
+    L = opt.lighting.shape[0]
+    transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
+    pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
+    gradient = np.zeros(mesh.v.shape, dtype=np.double, order='C')
+    lo, hi, res = _bounds(opt)
+    renderer.renderStreamedShadingGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, mesh.vn, opt.sample_num, lo, hi, res, transient,
+                                           pathlengths, gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag,
+                                           getattr(opt, 'loss_flag', 0))
+    return transient, gradient, pathlengths
+
+
+def inverseRenderingAlpha(mesh, data, weight, opt):
+    """:232-238"""
+    L = opt.lighting.shape[0]
+    transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
+    pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
+    lo, hi, res = _bounds(opt)
+    g = ggx.renderStreamedGradientAlpha(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, mesh.alpha, opt.sample_num, lo, hi, res, transient,
+                                        pathlengths, data, weight, opt.bin_refine_resolution, opt.sigma_bin)
+    return transient, g
+
+
+def inverseRenderingAlbedo(mesh, data, weight, opt):
+    """:241-250"""
+    L = opt.lighting.shape[0]
+    transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
+    pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
+    albedo = np.ones(mesh.v.shape[0], dtype=np.float32, order='C') * mesh.albedo
+    lo, hi, res = _bounds(opt)
+    g = renderer.renderStreamedGradientAlbedo(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, albedo.astype(np.float32), opt.sample_num, lo, hi, res,
+                                              transient, pathlengths, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag,
+                                              getattr(opt, 'loss_flag', 0))
+    return transient, g
+
+
+def inverseRendering(mesh, data, weight, opt):
+    """:252-269 — THE hot entry point: forward transient + vertex gradient."""
+    L = opt.lighting.shape[0]
+    transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
+    pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
+    gradient = np.zeros(mesh.v.shape, dtype=np.double, order='C')
+    lo, hi, res = _bounds(opt)
+    if getattr(opt, 'alpha_flag', False):
+        ggx.renderStreamedGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, mesh.alpha, opt.sample_num, lo, hi, res, transient, pathlengths,
+                                   gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag)
+    elif getattr(opt, 'jitter', False):
+        raise NotImplementedError('the SPAD-jitter temporal kernel (jitter/) is out of scope for this build (SURVEY.md 8f row N3)')
+    elif getattr(opt, 'albedo_flag', False):
+        albedo = (np.ones(mesh.v.shape[0], dtype=np.float32, order='C') * mesh.albedo).astype(np.float32)
+        renderer.renderStreamedGradientWithAlbedo(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, albedo, opt.sample_num, lo, hi, res, transient,
+                                                  pathlengths, gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag,
+                                                  getattr(opt, 'loss_flag', 0))
+    else:
+        renderer.renderStreamedGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, res, transient, pathlengths,
+                                        gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag, getattr(opt, 'loss_flag', 0))
+    return transient, gradient, pathlengths
+
+
+def removeTriangle(mesh, opt):
+    """:271-278 — drops faces that no wall point ever sees (unless all three neighbours exist)."""
+    intensity = np.zeros(mesh.f.shape[0], dtype=np.double, order='C')
+    lo, hi, _ = _bounds(opt)
+    renderer.renderStreamedTriangleIntensity(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, intensity)
+    threshold = 0
+    keep_face = np.logical_or((intensity > threshold), np.sum(mesh.f_affinity < 0, axis=1) == 0)
+    print('remove #face:%d' % (mesh.f.shape[0] - np.sum(keep_face)))
+    mesh.f = np.ascontiguousarray(mesh.f[keep_face, :])
+
+
+def forwardRendering(mesh, opt):
+    """:280-297 (the reference's *Shading branches omit refine_scale/sigma_bin — stale; (1,1) is passed here)."""
+    L = opt.lighting.shape[0]
+    transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
+    pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
+    lo, hi, res = _bounds(opt)
+    fn = getattr(opt, 'normal', 'fn') == 'fn'
+    if getattr(opt, 'alpha_flag', False):
+        if fn:
+            ggx.renderStreamedTransient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, mesh.alpha, opt.sample_num, lo, hi, res, transient, pathlengths, 1, 1)
+        else:
+            ggx.renderStreamedTransientShading(opt.lighting, opt.lighting_normal, mesh.v, mesh.vn, mesh.f, mesh.alpha, opt.sample_num, lo, hi, res, transient, pathlengths, 1, 1)
+    else:
+        if fn:
+            renderer.renderStreamedTransient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, res, transient, pathlengths, 1, 1)
+        else:
+            renderer.renderStreamedTransientShading(opt.lighting, opt.lighting_normal, mesh.v, mesh.vn, mesh.f, opt.sample_num, lo, hi, res, transient, pathlengths, 1, 1)
+    return transient, pathlengths
+
+
+def evaluate_loss_with_normal_smoothness(gt_transient, weight, transient, smoothing_val, mesh, render_opt):
+    """:360-367 (pure NumPy)."""
+    difference = transient - gt_transient
+    difference *= np.sqrt(weight)
+    L1 = np.linalg.norm(difference) ** 2 / difference.shape[0]
+    L2 = render_opt.smooth_weight * smoothing_val
+    return L1 + L2, L1

@@ -252,3 +252,52 @@ def test_edge_cases(gpu_ctx):
     T2 = np.zeros((4, B2)); pl2 = np.zeros(B2)
     renderer.renderStreamedTransient(o, n, v, f, 64, 0.0, 0.12, RES, T2, pl2, 1, 1, ctx=gpu_ctx)
     assert T2.sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ full-size goldens
+def _vis_digest(vis):
+    import zlib
+    L = vis.shape[0]; flat = vis.reshape(L, -1)
+    pop = flat.sum(axis=1).astype(np.int64)
+    crc = np.array([zlib.crc32(np.packbits(flat[i]).tobytes()) for i in range(L)], dtype=np.uint32)
+    return pop, crc
+
+
+@pytest.mark.parametrize('fixture', ['c_bunny16', 'c_bunny'])
+def test_c_bunny_against_committed_oracle_goldens(fixture, gpu_ctx):
+    """BASELINE.json configs[1] at full size (bunny, 64x64 wall, spp=1, r=10, s=1) against oracle output committed under
+    tests/golden (tools/make_golden.py): per-sample visibility digests bit-exact, transient <= 1e-5, gradient <= 1e-4."""
+    import os
+    import nlos_surface_optimization_b200 as nb
+    from nlos_surface_optimization_b200 import renderer, scenes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fixture + '.npz'))
+    wall, ns = int(g['wall']), int(g['num_sample'])
+    v, f = scenes.bunny(); o, n = scenes.wall_grid(wall)
+    L, B = o.shape[0], 1200
+    # target = the displaced mesh rendered by the GPU path; its marginals must match the oracle's
+    v2 = v.copy(); v2[:, 2] += 0.01
+    data = np.zeros((L, B)); pl = np.zeros(B)
+    renderer.renderStreamedTransient(o, n, v2, f, ns, LB, UB, RES, data, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(data.sum(1), g['data_row_sum']) <= TOL_TRANSIENT and rel_l2(data.sum(0), g['data_col_sum']) <= TOL_TRANSIENT
+    weight = np.ones_like(data)
+    T = np.zeros((L, B)); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T[g['rows']], g['transient_rows']) <= TOL_TRANSIENT
+    assert rel_l2(T.sum(1), g['transient_row_sum']) <= TOL_TRANSIENT
+    assert rel_l2(T.sum(0), g['transient_col_sum']) <= TOL_TRANSIENT
+    assert abs((T * T).sum() - float(g['transient_sq_sum'])) <= 2 * TOL_TRANSIENT * float(g['transient_sq_sum'])
+    assert np.array_equal((T > 0).sum(1), g['transient_nnz'])
+    assert rel_l2(G, g['gradient']) <= TOL_GRADIENT
+    # per-sample visibility, digested per source (popcount + crc32 of the packed bits), in slabs to bound host memory
+    slab = 256
+    for a in range(0, L, slab):
+        vis, _ = nb.debug_visibility(np.ascontiguousarray(o[a:a + slab]), v, f, ns, ctx=_windowed(gpu_ctx, a, L))
+        pop, crc = _vis_digest(vis)
+        assert np.array_equal(pop, g['vis_pop'][a:a + slab])
+        assert np.array_equal(crc, g['vis_crc'][a:a + slab])
+    gpu_ctx.set_source_window(0, 0)
+
+
+def _windowed(ctx, offset, total):
+    ctx.set_source_window(offset, total)
+    return ctx
