@@ -108,6 +108,9 @@ int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
   return c;
 }
 
+// forward kernel: sample slots (source*spp + k) per warp pass, bounded by the visibility tile in shared memory
+int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 256; return std::min(std::max(c, 1), 256); }
+
 void run_job(Ctx& cx, const Job& j) {
   NLOS_CUDA_OK(cudaSetDevice(cx.device));
   NLOS_REQUIRE(j.L >= 0 && j.V >= 0 && j.F >= 0, "negative size");
@@ -185,7 +188,7 @@ void run_job(Ctx& cx, const Job& j) {
     }
 
     if (j.kind == 3) {
-      P.chunk = auto_chunk(cx, "chunk_forward", j.F, j.L, cx.chunk_forward > 0 ? cx.chunk_forward : 128);
+      P.chunk = forward_chunk(cx);
       launch_intensity(cx, sc, P, j.ggx, o_I.dev);
       if (timing) { NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[4], st)); }
     } else {
@@ -193,7 +196,7 @@ void run_job(Ctx& cx, const Job& j) {
       uint32_t* vis = nullptr;
       const bool want_grad = j.kind >= 0 && j.kind <= 2;
       if (want_grad && cx.reuse_visibility) vis = cx.buf("vis").as<uint32_t>((size_t)j.L * P.spp * P.words_per_row);
-      P.chunk = auto_chunk(cx, "chunk_forward", j.F, j.L, cx.chunk_forward > 0 ? cx.chunk_forward : 128);
+      P.chunk = forward_chunk(cx);                                                       // sample slots per warp pass
       launch_forward(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
       if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st));
       if (want_grad) {

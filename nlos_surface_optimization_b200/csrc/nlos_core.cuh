@@ -186,6 +186,41 @@ NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restric
   }
 }
 
+// "while-while" variant used by the hot forward kernel: every lane first walks internal nodes until it holds a leaf
+// run (or is done), then all lanes test their leaf triangles together — the warp executes box tests with box tests and
+// triangle tests with triangle tests instead of interleaving them per lane.  Same answer as occluded().
+constexpr int kSentinel = 0x7fffffff;
+NLOS_HD int child_ref(int link, int cnt) { return cnt > 0 ? ~((link << 2) | (cnt - 1)) : link; }   // leaf run -> negative
+
+NLOS_HD bool occluded_ww(const BvhNode* __restrict__ nodes, const float4* __restrict__ ttris, int root_count,
+                         const Ray& r, float t_self, int prim_self) {
+  const float tlim = t_self * 1.000001f;
+  int stack[kStack]; int sp = 0;
+  int cur = root_count > 0 ? child_ref(0, root_count) : 0;
+  while (cur != kSentinel) {
+    while ((unsigned)cur < (unsigned)kSentinel) {                    // internal node
+      const float4 a = NLOS_LDG4(&nodes[cur].a), b = NLOS_LDG4(&nodes[cur].b), c = NLOS_LDG4(&nodes[cur].c);
+      const int4 d = *reinterpret_cast<const int4*>(&nodes[cur].d);
+      float t0, t1;
+      const bool h0 = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
+      const bool h1 = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
+      const int r0 = child_ref(d.x, d.z), r1 = child_ref(d.y, d.w);
+      if (h0 && h1) {
+        const bool first0 = t0 <= t1;
+        stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1;
+      } else if (h0) cur = r0;
+      else if (h1) cur = r1;
+      else cur = sp ? stack[--sp] : kSentinel;
+    }
+    while (cur < 0) {                                                // leaf run of 1..4 triangles
+      const int enc = ~cur; const int first = enc >> 2, cnt = (enc & 3) + 1;
+      for (int j = 0; j < cnt; ++j) if (tri_occludes(ttris, first + j, r, t_self, prim_self)) return true;
+      cur = sp ? stack[--sp] : kSentinel;
+    }
+  }
+  return false;
+}
+
 // ------------------------------------------------------------------ LBVH construction helpers (Karras 2012)
 NLOS_HD uint32_t expand_bits10(uint32_t v) {
   v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;

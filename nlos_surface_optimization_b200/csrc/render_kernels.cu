@@ -51,67 +51,162 @@ template <bool HAS_VA>
 __device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGeom& g) { return HAS_VA ? blend1(g.u, t.a1, g.v, t.a2, g.w, t.a3) : 1.0f; }
 
 // ---------------------------------------------------------------------------------------------- K1 forward
+// Warp-level two-phase kernel (DESIGN.md "Forward kernel"):
+//   phase A (generate): lane <-> triangle.  Every lane draws the sample of the next slot (slot = source*spp + k), runs
+//     the self intersection and the shading that needs no visibility; samples that can contribute (front-facing, in
+//     range) are COMPACTED into a per-warp ray queue in shared memory (ballot + popc).
+//   phase B (trace): whenever 32 rays are queued (or the slots are exhausted) each lane pops one ray — of any triangle
+//     of the tile — and runs the any-hit traversal; visible rays add their value to the transient row (FP64 RED) and
+//     set their bit in the warp's visibility tile.
+// Back-facing / out-of-range samples therefore never occupy a lane during traversal, which is where the time goes.
+constexpr int kQCap = 64;        // ray queue capacity per warp (power of two, >= 63)
+constexpr int kTile = 256;       // sample slots per warp pass == visibility words in the warp tile
+constexpr int kRefill = 8;       // idle lanes that trigger a refill of the traversal lanes from the queue
+constexpr int kDone = (int)0x80000000;   // traversal state: stack exhausted, no occluder found (never a valid leaf ref)
+struct WarpShared {
+  float dx[kQCap], dy[kQCap], dz[kQCap], ts[kQCap], val[kQCap];
+  int bin[kQCap];                // histogram bin of the sample (-1: outside the histogram)
+  int meta[kQCap];               // slot_local | tri_lane << 16
+  unsigned tile[kTile];          // one visibility word (32 triangles) per slot
+};
+
 // MODE 0: transient histogram (+ optional visibility bits);  MODE 1: per-triangle intensity (K6)
 template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
 __global__ void __launch_bounds__(kBlock) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix) {
-  extern __shared__ double s_w[];           // SMOOTH: prefix sums of the Gaussian taps, K+1 entries
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared* ws_all = reinterpret_cast<WarpShared*>(smem_raw);
+  double* s_w = reinterpret_cast<double*>(smem_raw + (kBlock / 32) * sizeof(WarpShared));   // SMOOTH: tap prefix sums
   if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += blockDim.x) s_w[i] = wprefix[i]; __syncthreads(); }
+  const int lane = threadIdx.x & 31;
+  WarpShared& ws = ws_all[threadIdx.x >> 5];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = p < sc.F;
+  const int warp_global = p >> 5;
   TriRegs t;
+  t.prim = 0;
   if (active) load_tri<HAS_VN, HAS_VA>(sc, p, t);
-  const int64_t s0 = (int64_t)blockIdx.y * P.chunk;
-  const int64_t s1 = s0 + P.chunk < P.L ? s0 + P.chunk : P.L;
   const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
   const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
-  const int lane = threadIdx.x & 31;
-  const int warp_global = p >> 5;
-  double acc = 0.0;                         // MODE 1
-  for (int64_t s = s0; s < s1; ++s) {
-    const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
-    const f3 o = xyz(o4), on = xyz(n4);
-    for (int k = 0; k < P.spp; ++k) {
-      bool bit = false;
-      SampleGeom g;
-      if (active && sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
-        const f3 n = shading_normal<HAS_VN>(t, g);
-        float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;        // TG.cpp:224-227
-        if (ff > 0.0f) {                                              // max(0,ff)==0 adds exactly 0 (TG.cpp:228)
-          const Ray ray = make_ray(o, g.d);
-          if (!occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim)) {
-            bit = true;
-            const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
-            float val = t.st.A * alb * ff * ff;
-            if (GGX) val = val * ggx_eval(P.alpha, dot3(n, -g.d));    // ggx/TG.cpp:236-238
-            const double dv = (double)val / (double)P.spp;
-            if (MODE == 1) acc += dv;
-            else {
-              const int64_t bin = (int64_t)floorf((2.0f * g.r - P.lb) / P.res_fwd);   // TG.cpp:229
-              if (bin >= 0 && bin < nbf) {
-                if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
-                else {
-                  const int half = 2 * P.r_fwd * P.s_bin;
-                  int64_t b0 = floordiv(bin - half, P.r_fwd), b1 = floordiv(bin + half, P.r_fwd);
-                  if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
-                  for (int64_t b = b0; b <= b1; ++b) {
-                    int ilo, ihi; tap_span(bin, (int)b, P.r_fwd, half, P.K, ilo, ihi);
-                    const double wsum = s_w[ihi] - s_w[ilo];
-                    if (ihi > ilo) atomicAdd(out + s * P.numBins + b, dv * wsum);
-                  }
+  const int64_t total_slots = P.L * (int64_t)P.spp;
+  const int64_t nchunks = (total_slots + P.chunk - 1) / P.chunk;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
+    const int64_t slot0 = chunk * P.chunk;
+    const int nslots = (int)(total_slots - slot0 < P.chunk ? total_slots - slot0 : P.chunk);
+    if (WRITE_VIS) { for (int i = lane; i < nslots; i += 32) ws.tile[i] = 0u; }
+    __syncwarp();
+    int gen = 0, qhead = 0, qcount = 0;
+    // per-lane traversal state of the ray in flight (cur == kSentinel: lane is idle)
+    int cur = kSentinel, sp = 0, stack[kStack];
+    Ray ray; float ts = 0.f, val = 0.f; int bin = -1, prim = 0, tri_lane = 0, slot_local = 0; int64_t src = 0;
+    ray.o = ray.d = ray.id = ray.oid = mk3(0.f, 0.f, 0.f);
+    for (;;) {
+      const unsigned idle_mask = __ballot_sync(0xffffffffu, cur == kSentinel);
+      const int n_idle = __popc(idle_mask);
+      if (n_idle >= kRefill) {
+        // ---------------- phase A: generate + compact until the idle lanes can be fed
+        while (qcount < n_idle && gen < nslots) {
+          const int64_t slot = slot0 + gen;
+          const int64_t s = P.spp == 1 ? slot : slot / P.spp;
+          const int k = P.spp == 1 ? 0 : (int)(slot - s * P.spp);
+          bool need = false;
+          float r_dx = 0.f, r_dy = 0.f, r_dz = 0.f, r_ts = 0.f, r_val = 0.f; int r_bin = -1;
+          if (active) {
+            const f3 o = xyz(__ldg(P.origin + s)), on = xyz(__ldg(P.onormal + s));
+            SampleGeom g;
+            if (sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
+              const f3 n = shading_normal<HAS_VN>(t, g);
+              const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
+              if (ff > 0.0f) {                                                      // max(0,ff)==0 adds exactly 0 (TG.cpp:228)
+                const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
+                float v = t.st.A * alb * ff * ff;
+                if (GGX) v = v * ggx_eval(P.alpha, dot3(n, -g.d));                  // ggx/TG.cpp:236-238
+                if (MODE == 0) {
+                  const int64_t b = (int64_t)floorf((2.0f * g.r - P.lb) / P.res_fwd);   // TG.cpp:229
+                  r_bin = (b >= 0 && b < nbf) ? (int)b : -1;
                 }
+                need = true; r_dx = g.d.x; r_dy = g.d.y; r_dz = g.d.z; r_ts = g.t; r_val = v;
               }
             }
           }
+          const unsigned mask = __ballot_sync(0xffffffffu, need);
+          if (need) {
+            const int pos = (qhead + qcount + __popc(mask & lt)) & (kQCap - 1);
+            ws.dx[pos] = r_dx; ws.dy[pos] = r_dy; ws.dz[pos] = r_dz; ws.ts[pos] = r_ts; ws.val[pos] = r_val; ws.bin[pos] = r_bin;
+            ws.meta[pos] = gen | (lane << 16);
+          }
+          qcount += __popc(mask); ++gen;
         }
+        __syncwarp();
+        // ---------------- refill: idle lanes pop rays (of any triangle of the tile)
+        const int take = n_idle < qcount ? n_idle : qcount;
+        if (take == 0 && n_idle == 32) break;                  // slots exhausted, queue empty, nobody tracing
+        const int rank = __popc(idle_mask & lt);
+        const bool fetch = cur == kSentinel && rank < take;
+        int meta = 0;
+        if (fetch) {
+          const int pos = (qhead + rank) & (kQCap - 1);
+          meta = ws.meta[pos];
+          ts = ws.ts[pos]; val = ws.val[pos]; bin = ws.bin[pos];
+          slot_local = meta & 0xffff; tri_lane = (meta >> 16) & 31;
+          const int64_t slot = slot0 + slot_local;
+          src = P.spp == 1 ? slot : slot / P.spp;
+          ray = make_ray(xyz(__ldg(P.origin + src)), mk3(ws.dx[pos], ws.dy[pos], ws.dz[pos]));
+          sp = 0; cur = sc.root_count > 0 ? child_ref(0, sc.root_count) : 0;
+        }
+        const int prim_new = __shfl_sync(0xffffffffu, t.prim, (meta >> 16) & 31);
+        if (fetch) prim = prim_new;
+        qhead = (qhead + take) & (kQCap - 1); qcount -= take;
+        __syncwarp();                            // pops complete before the next phase A overwrites the ring
       }
-      if (WRITE_VIS) {
-        const unsigned m = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0) vis[((size_t)s * P.spp + k) * P.words_per_row + warp_global] = m;
+      // ---------------- one traversal round: internal nodes until a leaf run, then that leaf run
+      const float tlim = ts * 1.000001f;
+      while ((unsigned)cur < (unsigned)kSentinel) {
+        const float4 a = __ldg(&sc.nodes[cur].a), b = __ldg(&sc.nodes[cur].b), c = __ldg(&sc.nodes[cur].c);
+        const int4 d = __ldg(&sc.nodes[cur].d);
+        float t0, t1;
+        const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
+        const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
+        const int r0 = child_ref(d.x, d.z), r1 = child_ref(d.y, d.w);
+        if (h0 && h1) { const bool first0 = t0 <= t1; stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1; }
+        else if (h0) cur = r0;
+        else if (h1) cur = r1;
+        else cur = sp ? stack[--sp] : kDone;
+      }
+      if (cur < 0 && cur != kDone) {
+        const int enc = ~cur; const int first = enc >> 2, cnt = (enc & 3) + 1;
+        bool occ = false;
+        for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes(sc.ttris, first + j, ray, ts, prim);
+        cur = occ ? kSentinel : (sp ? stack[--sp] : kDone);      // occluded: drop the ray
+      }
+      if (cur == kDone) {                                        // traversal finished without an occluder: visible
+        const double dv = (double)val / (double)P.spp;           // TG.cpp:231-232
+        if (MODE == 1) atomicAdd(out + prim, dv);
+        else if (bin >= 0) {
+          if (!SMOOTH) atomicAdd(out + src * P.numBins + bin, dv);
+          else {
+            // Gaussian smoothing + downsampling of TG.cpp:348-371 applied per sample: tap i of fine bin m lands in
+            // coarse bin floor((m + i - 2rs)/r); the taps of one coarse bin are a contiguous run -> prefix sums
+            const int half = 2 * P.r_fwd * P.s_bin;
+            int64_t b0 = floordiv((int64_t)bin - half, P.r_fwd), b1 = floordiv((int64_t)bin + half, P.r_fwd);
+            if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+            for (int64_t b = b0; b <= b1; ++b) {
+              int ilo, ihi; tap_span(bin, (int)b, P.r_fwd, half, P.K, ilo, ihi);
+              if (ihi > ilo) atomicAdd(out + src * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
+            }
+          }
+        }
+        if (WRITE_VIS) atomicOr(&ws.tile[slot_local], 1u << tri_lane);
+        cur = kSentinel;
       }
     }
+    if (WRITE_VIS) {
+      __syncwarp();
+      if (warp_global * 32 < sc.F) for (int i = lane; i < nslots; i += 32) vis[(size_t)(slot0 + i) * P.words_per_row + warp_global] = ws.tile[i];
+      __syncwarp();
+    }
   }
-  if (MODE == 1 && active && acc != 0.0) atomicAdd(out + t.prim, acc);
 }
 
 // ---------------------------------------------------------------------------------------------- K3 residual
@@ -294,8 +389,9 @@ inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
 
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
-  const dim3 grid = sample_grid(sc, P);
-  const size_t smem = SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0;
+  const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
+  const dim3 grid((unsigned)((sc.F + kBlock - 1) / kBlock), (unsigned)std::min<int64_t>(nchunks, 65535), 1);
+  const size_t smem = (kBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
   if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   cx.launches += 1;

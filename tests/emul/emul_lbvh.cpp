@@ -119,6 +119,7 @@ long emul_visibility(const float* origin, int L, const float* verts, int V, cons
           Ray ray = make_ray(o, g.d);
           uint32_t cb = 0, ct = 0;
           bool occ = occluded(b.nodes.data(), b.ttris.data(), b.root_count, ray, g.t, prim, &cb, &ct);
+          if (occluded_ww(b.nodes.data(), b.ttris.data(), b.root_count, ray, g.t, prim) != occ) ++mism;   // both traversal orders agree
           nb += cb; nt += ct; nr++;
           bit = occ ? 0 : 1;
           if (check_brute) {
