@@ -102,6 +102,25 @@ int nlos_streamed_render_gradient_albedo(nlos_ctx* ctx, const double* data, cons
                                          double* transient, double* pathlengths, int refine_scale, int sigma_bin,
                                          int testing_flag, int loss_test, int numBins, double* result /*host*/);
 
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:9  streamed_render_vertex_gradient
+ * (renderer.pyx:78 renderStreamedVertexGradient — the Python side hard-codes measurement = 1, renderer.pyx:88);
+ * gradient[B,3] = per-time-bin gradient of vertex `vertex_num`, accumulated into */
+int nlos_streamed_render_vertex_gradient(nlos_ctx* ctx, int vertex_num, const float* originD, int measurement, const float* normalD,
+                                         const float* verticesD, int numVertices, const int* trianglesD, int numTriangles,
+                                         int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                         float pathlengthResolution, double* gradient, int refine_scale, int sigma_bin, int numBins);
+
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:11  streamed_render_normal_smoothing (renderer.pyx:13);
+ * the reference returns the regulariser value; curvature_grad[V,3] is overwritten.  Per-vertex writes use '=' in the
+ * reference (last adjacent face wins, scheduler dependent); here the adjacent face with the highest index wins. */
+int nlos_streamed_render_normal_smoothing(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD,
+                                          int numTriangles, const int* face_affinity, double* curvature_grad,
+                                          double* value_out /*host*/);
+
+/* smoothed_transient/stratifiedStreamedGradientRenderer.h:13  streamed_render_curvature_grad (renderer.pyx:26) */
+int nlos_streamed_render_curvature_grad(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD,
+                                        int numTriangles, double* curvature_grad);
+
 /* ---- module `ggx` (ggx/) -------------------------------------------------------------------------- */
 
 /* ggx/stratifiedStreamedTransientRenderer.h:4  streamed_render_transient (ggx.pyx:118, :82, :100) */

@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnlos_b200.so')
+LIB_PATH = os.environ.get('NLOS_B200_LIB', os.path.join(_HERE, 'libnlos_b200.so'))   # override: A/B builds of the kernels
 
 NLOS_OK, NLOS_ERR_INVALID, NLOS_ERR_CUDA, NLOS_ERR_NOMEM = 0, 1, 2, 3
 
@@ -48,6 +48,10 @@ SIGNATURES = {
                                                          C.c_float, _d, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'nlos_streamed_render_gradient_albedo': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float,
                                                        C.c_float, _d, _d, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _d]),
+    'nlos_streamed_render_vertex_gradient': (C.c_int, [_ctx, C.c_int, _f, C.c_int, _f, _f, C.c_int, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                       _d, C.c_int, C.c_int, C.c_int]),
+    'nlos_streamed_render_normal_smoothing': (C.c_int, [_ctx, _f, C.c_int, _i, C.c_int, _i, _d, _d]),
+    'nlos_streamed_render_curvature_grad': (C.c_int, [_ctx, _f, C.c_int, _i, C.c_int, _d]),
     'nlos_ggx_streamed_render_transient': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
                                                      C.c_float, _d, _d, C.c_int, C.c_int, C.c_int]),
     'nlos_ggx_streamed_render_intensity': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, _d]),

@@ -69,7 +69,7 @@ bool finish_out(Ctx& cx, const OutView<T>& v) {
 }
 
 // Gaussian taps exactly as the reference builds them (TG.cpp:537-544, :350-355) plus their prefix sums
-struct TapTables { int K = 1; double sigma2 = 1; std::vector<double> wprefix, dprefix; };
+struct TapTables { int K = 1; double sigma2 = 1; std::vector<double> w, wprefix, dprefix; };
 TapTables make_taps(float res, int r, int s) {
   TapTables t; t.K = 4 * r * s + 1;
   const double sigma = res * s / 2.355;
@@ -80,6 +80,7 @@ TapTables make_taps(float res, int r, int s) {
     const double x = (-2 * r * s + i) * res / r / sigma;
     const double w = std::exp(-(x * x) / 2) * norm;
     const double delta = (double)(((float)(-2 * r * s + i) * res) / (float)r);     // TG.cpp:973 (float expression)
+    t.w.push_back(w);
     t.wprefix[i + 1] = t.wprefix[i] + w;
     t.dprefix[i + 1] = t.dprefix[i] + w * delta;
   }
@@ -408,6 +409,79 @@ int nlos_ggx_streamed_render_gradient_alpha(nlos_ctx* ctx, const double* data, c
   j.data = data; j.weight = weight; j.transient = transient; j.pathlengths = pathlengths; j.scalar_out = result;
   j.kind = 2; j.ggx = true; j.alpha = alpha;
   return guarded(ctx, j);
+}
+
+
+int nlos_streamed_render_vertex_gradient(nlos_ctx* ctx, int vertex_num, const float* originD, int measurement, const float* normalD, const float* verticesD,
+                                         int numVertices, const int* trianglesD, int numTriangles, int numSamples, float lb, float ub, float res,
+                                         double* gradient, int refine_scale, int sigma_bin, int numBins) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_REQUIRE(originD && normalD && verticesD && trianglesD && gradient, "null argument");
+    NLOS_REQUIRE(measurement > 0 && numVertices > 0 && numTriangles > 0 && numBins > 0 && res > 0.f && refine_scale >= 1 && sigma_bin >= 1, "bad size");
+    cudaStream_t st = cx.stream;
+    const int64_t L = measurement; const int F = numTriangles;
+    const float* d_origin = stage_in(cx, "in_origin", originD, 3 * (size_t)L, st);
+    const float* d_onormal = stage_in(cx, "in_onormal", normalD, 3 * (size_t)L, st);
+    const float* d_verts = stage_in(cx, "in_verts", verticesD, 3 * (size_t)numVertices, st);
+    const int* d_faces = stage_in(cx, "in_faces", trianglesD, 3 * (size_t)F, st);
+    OutView<double> o_G = stage_out(cx, "out_vgrad", gradient, 3 * (size_t)numBins, true);
+    DeviceScene sc; build_scene(cx, d_verts, numVertices, d_faces, F, d_origin, L, nullptr, nullptr, sc);
+    float4* origin4 = cx.buf("origin4").as<float4>((size_t)L); float4* onormal4 = cx.buf("onormal4").as<float4>((size_t)L);
+    launch_pack4(cx, d_origin, origin4, (size_t)L); launch_pack4(cx, d_onormal, onormal4, (size_t)L);
+    RenderParams P; std::memset(&P, 0, sizeof P);
+    P.origin = origin4; P.onormal = onormal4; P.L = L; P.src_offset = cx.src_offset; P.seed = cx.seed;
+    P.spp = std::max(1, 1 + (numSamples - 1) / F);
+    P.lb = lb; P.ub = ub; P.res = res; P.numBins = numBins; P.r_grad = refine_scale; P.s_bin = sigma_bin; P.K = 4 * refine_scale * sigma_bin + 1;
+    TapTables taps = make_taps(res, refine_scale, sigma_bin);
+    double* d_taps = cx.buf("taps").as<double>(taps.w.size());
+    NLOS_CUDA_OK(cudaMemcpyAsync(d_taps, taps.w.data(), taps.w.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* acc = cx.buf("vgrad_acc").as<double>(3 * (size_t)numBins);
+    NLOS_CUDA_OK(cudaMemsetAsync(acc, 0, 3 * (size_t)numBins * sizeof(double), st));
+    launch_vertex_gradient(cx, sc, P, vertex_num, d_taps, taps.sigma2, acc);
+    launch_finalize_gradient(cx, acc, o_G.dev, 3 * (size_t)numBins, 1.0 / (double)L);     // TG.cpp:431-435
+    if (finish_out(cx, o_G)) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    cx.last_error.clear();
+    return NLOS_OK;
+  } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
+  catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
+static int run_regulariser(nlos_ctx* ctx, int mode, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles,
+                           const int* face_affinity, double* grad, double* value_out) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_REQUIRE(verticesD && trianglesD && grad && (mode == 1 || face_affinity), "null argument");
+    NLOS_REQUIRE(numVertices > 0 && numTriangles >= 0, "bad size");
+    cudaStream_t st = cx.stream;
+    const float* d_verts = stage_in(cx, "in_verts", verticesD, 3 * (size_t)numVertices, st);
+    const int* d_faces = stage_in(cx, "in_faces", trianglesD, 3 * (size_t)numTriangles, st);
+    const int* d_aff = mode == 0 ? stage_in(cx, "in_aff", face_affinity, 3 * (size_t)numTriangles, st) : nullptr;
+    OutView<double> o_G = stage_out(cx, "out_reg", grad, 3 * (size_t)numVertices, false);
+    double* d_val = cx.buf("reg_value").as<double>(1);
+    launch_regulariser(cx, mode, d_verts, numVertices, d_faces, numTriangles, d_aff, o_G.dev, d_val);
+    finish_out(cx, o_G);
+    double h = 0;
+    if (value_out) NLOS_CUDA_OK(cudaMemcpyAsync(&h, d_val, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (value_out || o_G.host) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    if (value_out) *value_out = h;
+    cx.last_error.clear();
+    return NLOS_OK;
+  } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
+  catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
+int nlos_streamed_render_normal_smoothing(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles,
+                                          const int* face_affinity, double* curvature_grad, double* value_out) {
+  return run_regulariser(ctx, 0, verticesD, numVertices, trianglesD, numTriangles, face_affinity, curvature_grad, value_out);
+}
+
+int nlos_streamed_render_curvature_grad(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles, double* curvature_grad) {
+  return run_regulariser(ctx, 1, verticesD, numVertices, trianglesD, numTriangles, nullptr, curvature_grad, nullptr);
 }
 
 int nlos_debug_visibility(nlos_ctx* ctx, const float* originD, int numSources, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles,

@@ -144,14 +144,23 @@ NLOS_HD bool slab(const Ray& r, float lox, float loy, float loz, float hix, floa
 #define NLOS_LDG4(p) (*(p))
 #endif
 
+// 32-byte read-only load (one LDG.E.256 on sm_100a: half the L1 wavefronts of two LDG.128); p must be 32-byte aligned
+NLOS_HD void ld256(const float4* __restrict__ p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__)
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+  a = p[0]; b = p[1];
+#endif
+}
+
 // does triangle j (sorted index) beat (t_self, prim_self) in the lexicographic nearest-hit order?
 NLOS_HD bool tri_occludes(const float4* __restrict__ ttris, int j, const Ray& r, float t_self, int prim_self) {
-  const float4 q0 = NLOS_LDG4(ttris + 4 * (size_t)j);
+  float4 q0, q1, q2, q3;
+  ld256(ttris + 4 * (size_t)j, q0, q1);
+  ld256(ttris + 4 * (size_t)j + 2, q2, q3);
   const int prim = f2i(q0.w);
   if (prim == prim_self) return false;
-  const float4 q1 = NLOS_LDG4(ttris + 4 * (size_t)j + 1);
-  const float4 q2 = NLOS_LDG4(ttris + 4 * (size_t)j + 2);
-  const float4 q3 = NLOS_LDG4(ttris + 4 * (size_t)j + 3);
   TriRec tr; tr.v0 = xyz(q0); tr.e1 = xyz(q1); tr.e2 = xyz(q2); tr.Ng = xyz(q3);
   float t, u, v;
   if (!isect(tr, r.o, r.d, t, u, v)) return false;

@@ -61,7 +61,13 @@ __device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGe
 // Back-facing / out-of-range samples therefore never occupy a lane during traversal, which is where the time goes.
 constexpr int kQCap = 64;        // ray queue capacity per warp (power of two, >= 63)
 constexpr int kTile = 256;       // sample slots per warp pass == visibility words in the warp tile
-constexpr int kRefill = 8;       // idle lanes that trigger a refill of the traversal lanes from the queue
+#ifndef NLOS_REFILL
+#define NLOS_REFILL 16
+#endif
+#ifndef NLOS_FWD_MINBLOCKS
+#define NLOS_FWD_MINBLOCKS 4
+#endif
+constexpr int kRefill = NLOS_REFILL;   // idle lanes that trigger a refill of the traversal lanes from the queue
 constexpr int kDone = (int)0x80000000;   // traversal state: stack exhausted, no occluder found (never a valid leaf ref)
 struct WarpShared {
   float dx[kQCap], dy[kQCap], dz[kQCap], ts[kQCap], val[kQCap];
@@ -72,7 +78,7 @@ struct WarpShared {
 
 // MODE 0: transient histogram (+ optional visibility bits);  MODE 1: per-triangle intensity (K6)
 template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
-__global__ void __launch_bounds__(kBlock) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
+__global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* ws_all = reinterpret_cast<WarpShared*>(smem_raw);
@@ -163,8 +169,10 @@ __global__ void __launch_bounds__(kBlock) k_forward(const DeviceScene sc, const 
       // ---------------- one traversal round: internal nodes until a leaf run, then that leaf run
       const float tlim = ts * 1.000001f;
       while ((unsigned)cur < (unsigned)kSentinel) {
-        const float4 a = __ldg(&sc.nodes[cur].a), b = __ldg(&sc.nodes[cur].b), c = __ldg(&sc.nodes[cur].c);
-        const int4 d = __ldg(&sc.nodes[cur].d);
+        float4 a, b, c, dq;
+        ld256(&sc.nodes[cur].a, a, b);
+        ld256(&sc.nodes[cur].c, c, dq);
+        const int4 d = make_int4(__float_as_int(dq.x), __float_as_int(dq.y), __float_as_int(dq.z), __float_as_int(dq.w));
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
         const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);

@@ -13,5 +13,8 @@ void launch_finalize_gradient(Ctx& cx, const double* acc, double* gradient, size
 void launch_visibility(Ctx& cx, const DeviceScene& sc, const RenderParams& P, uint8_t* vis_out, unsigned long long* counters);
 void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n);
 void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res);
+// mesh_kernels.cu
+void launch_vertex_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, int vertex_num, const double* taps, double sigma2, double* acc);
+void launch_regulariser(Ctx& cx, int mode, const float* verts, int V, const int* faces, int F, const int* aff, double* grad, double* value);
 
 }  // namespace nlos

@@ -12,7 +12,8 @@ from ._arrays import as_pointer, num_bins
 
 __all__ = ['renderStreamedTransient', 'renderStreamedTransientShading', 'renderStreamedTransientwAlbedo',
            'renderStreamedGradient', 'renderStreamedShadingGradient', 'renderStreamedGradientWithAlbedo',
-           'renderStreamedGradientAlbedo', 'renderStreamedTriangleIntensity']
+           'renderStreamedGradientAlbedo', 'renderStreamedTriangleIntensity', 'renderStreamedVertexGradient', 'renderStreamedNormalSmoothing',
+           'renderStreamedCurvatureGradient']
 
 
 def _common(origin, normal, vertices, faces):
@@ -168,3 +169,52 @@ def renderStreamedTriangleIntensity(origin, normal, vertices, faces, num_sample,
     assert si[0] == F, "intensity should be (F,)"
     rc = cx.lib.nlos_streamed_render_intensity(cx.handle, po, L, pn, pv, V, None, pf, F, int(num_sample), float(lower_bound), float(upper_bound), pi)
     cx.check(rc, 'nlos_streamed_render_intensity')
+
+
+def renderStreamedVertexGradient(origin, normal, vertices, faces, num_sample, lower_bound, upper_bound, resolution, gradient, vertex_num,
+                                 refine_scale, sigma_bin, ctx=None):
+    """renderer.pyx:78 -> streamed_render_vertex_gradient with measurement = 1 (only origin[0] is used, renderer.pyx:88);
+    gradient[B,3] receives the per-time-bin gradient of vertex `vertex_num` (always with the normal-variation term)."""
+    cx = ctx or _ffi.default_context()
+    po, pn, pv, pf, L, V, F = _common(origin, normal, vertices, faces)
+    B = num_bins(lower_bound, upper_bound, resolution)
+    pg, sg = as_pointer(gradient, 'f64', 2, 'gradient')
+    assert sg[0] == B, "gradient dimension should be Vx3"
+    assert sg[1] == 3, "gradient dimension should be Vx3"
+    rc = cx.lib.nlos_streamed_render_vertex_gradient(cx.handle, int(vertex_num), po, 1, pn, pv, V, pf, F, int(num_sample), float(lower_bound),
+                                                     float(upper_bound), float(resolution), pg, int(refine_scale), int(sigma_bin), B)
+    cx.check(rc, 'nlos_streamed_render_vertex_gradient')
+
+
+def renderStreamedNormalSmoothing(vertices, faces, f_affinity, gradient, ctx=None):
+    """renderer.pyx:13 -> streamed_render_normal_smoothing; returns the regulariser value, fills gradient[V,3]."""
+    import ctypes as C
+    cx = ctx or _ffi.default_context()
+    pv, sv = as_pointer(vertices, 'f32', 2, 'vertices')
+    pf, sf = as_pointer(faces, 'i32', 2, 'faces')
+    pa, sa = as_pointer(f_affinity, 'i32', 2, 'f_affinity')
+    pg, sg = as_pointer(gradient, 'f64', 2, 'gradient')
+    assert sv[1] == 3, "vertices needs to be Vx3"
+    assert sf[1] == 3, "faces needs to be Fx3"
+    assert sa[1] == 3, "face affinity needs to be Fx3"
+    assert sa[0] == sf[0], "face affinity needs to be Fx3"
+    assert sg[0] == sv[0], "gradient dimension should be Vx3"
+    assert sg[1] == 3, "gradient dimension should be Vx3"
+    out = C.c_double(0.0)
+    rc = cx.lib.nlos_streamed_render_normal_smoothing(cx.handle, pv, sv[0], pf, sf[0], pa, pg, C.byref(out))
+    cx.check(rc, 'nlos_streamed_render_normal_smoothing')
+    return out.value
+
+
+def renderStreamedCurvatureGradient(vertices, faces, gradient, ctx=None):
+    """renderer.pyx:26 -> streamed_render_curvature_grad."""
+    cx = ctx or _ffi.default_context()
+    pv, sv = as_pointer(vertices, 'f32', 2, 'vertices')
+    pf, sf = as_pointer(faces, 'i32', 2, 'faces')
+    pg, sg = as_pointer(gradient, 'f64', 2, 'gradient')
+    assert sv[1] == 3, "vertices needs to be Vx3"
+    assert sf[1] == 3, "faces needs to be Fx3"
+    assert sg[0] == sv[0], "gradient dimension should be Vx3"
+    assert sg[1] == 3, "gradient dimension should be Vx3"
+    rc = cx.lib.nlos_streamed_render_curvature_grad(cx.handle, pv, sv[0], pf, sf[0], pg)
+    cx.check(rc, 'nlos_streamed_render_curvature_grad')

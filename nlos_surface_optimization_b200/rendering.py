@@ -131,6 +131,20 @@ def forwardRendering(mesh, opt):
     return transient, pathlengths
 
 
+def renderStreamedNormalSmoothing(mesh):
+    """:299-302"""
+    gradient = np.zeros(mesh.v.shape, dtype=np.double, order='C')
+    val = renderer.renderStreamedNormalSmoothing(mesh.v, mesh.f, mesh.f_affinity, gradient)
+    return val, gradient
+
+
+def renderStreamedCurvatureGradient(mesh):
+    """:304-307"""
+    gradient = np.zeros(mesh.v.shape, dtype=np.double, order='C')
+    renderer.renderStreamedCurvatureGradient(mesh.v, mesh.f, gradient)
+    return gradient
+
+
 def evaluate_loss_with_normal_smoothness(gt_transient, weight, transient, smoothing_val, mesh, render_opt):
     """:360-367 (pure NumPy)."""
     difference = transient - gt_transient

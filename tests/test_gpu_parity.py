@@ -301,3 +301,27 @@ def test_c_bunny_against_committed_oracle_goldens(fixture, gpu_ctx):
 def _windowed(ctx, offset, total):
     ctx.set_source_window(offset, total)
     return ctx
+
+
+def test_vertex_gradient_debug_and_regularisers(oracle, gpu_ctx):
+    from nlos_surface_optimization_b200 import renderer, scenes
+    v, f = scenes.fan8(); o, n = scenes.wall_grid(2)
+    ns = 8 * 200; B = 1200
+    ref = oracle.vertex_gradient(8, o, n, v, f, ns, LB, UB, RES, 10, 1)
+    G = np.zeros((B, 3))
+    renderer.renderStreamedVertexGradient(o, n, v, f, ns, LB, UB, RES, G, 8, 10, 1, ctx=gpu_ctx)
+    assert np.linalg.norm(ref) > 0 and rel_l2(G, ref) <= TOL_GRADIENT
+    for mesh in (scenes.icosphere(3, 0.1, (0, 0, 0.45), noise=0.05, seed=7), scenes.bunny()):
+        mv, mf = mesh
+        aff = scenes.face_affinity(mf) if mf.shape[0] < 5000 else -np.ones_like(mf)
+        if mf.shape[0] >= 5000:      # cheap synthetic adjacency for the big mesh: neighbours by index
+            aff = np.ascontiguousarray(np.stack([np.roll(np.arange(mf.shape[0]), 1), np.roll(np.arange(mf.shape[0]), -1), -np.ones(mf.shape[0])], axis=1).astype(np.int32))
+        val_ref, G_ref = oracle.normal_smoothing(mv, mf, aff)
+        Gn = np.full((mv.shape[0], 3), 5.0)
+        val = renderer.renderStreamedNormalSmoothing(mv, mf, aff, Gn, ctx=gpu_ctx)
+        assert abs(val - val_ref) <= 1e-9 * max(abs(val_ref), 1e-12)
+        assert np.array_equal(Gn, G_ref)
+        C_ref = oracle.curvature_grad(mv, mf)
+        Gc = np.full((mv.shape[0], 3), 5.0)
+        renderer.renderStreamedCurvatureGradient(mv, mf, Gc, ctx=gpu_ctx)
+        assert np.array_equal(Gc, C_ref)
