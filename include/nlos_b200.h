@@ -160,6 +160,11 @@ int nlos_ggx_streamed_render_gradient_alpha(nlos_ctx* ctx, const double* data, c
 int nlos_debug_visibility(nlos_ctx* ctx, const float* originD, int numSources, const float* verticesD, int numVertices,
                           const int* trianglesD, int numTriangles, int numSamples, uint8_t* visibility, uint64_t* counters3);
 
+/* Measured roofline denominators for this path: FP32 FFMA throughput in TFLOP/s and FP64 RED.ADD
+ * throughput in 1e9 atomics/s over `num_addresses` (rounded down to a power of two) hashed addresses. <0 on error. */
+double nlos_microbench_fp32(nlos_ctx* ctx);
+double nlos_microbench_red_f64(nlos_ctx* ctx, int64_t num_addresses);
+
 #ifdef __cplusplus
 }
 #endif

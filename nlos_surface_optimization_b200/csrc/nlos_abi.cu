@@ -12,7 +12,6 @@
 #include "nlos_ctx.h"
 #include "render_kernels.h"
 
-struct nlos_ctx { nlos::Ctx cx; };
 
 namespace nlos {
 

@@ -56,3 +56,6 @@ void build_scene(Ctx& cx, const float* d_verts, int V, const int* d_faces, int F
                  const float* d_vnormal, const float* d_valbedo, DeviceScene& out);
 
 }  // namespace nlos
+
+// the opaque handle of include/nlos_b200.h
+struct nlos_ctx { nlos::Ctx cx; };

@@ -36,22 +36,33 @@ def num(x):
 
 
 if sass:
-    rows = list(csv.reader(open(sass)))
-    hdr = rows[1]; data = rows[2:]; ix = {k: i for i, k in enumerate(hdr)}
-    tot_inst = sum(num(r[ix['Instructions Executed']]) for r in data); tot_samp = sum(num(r[ix['# Samples']]) for r in data)
-    st = [k for k in hdr if k.startswith('stall_') and 'Not Issued' not in k]
-    print('total warp inst %.4g, samples %d' % (tot_inst, tot_samp))
-    print('stall mix (all samples): ' + ' '.join('%s=%.1f%%' % (k[6:], 100 * sum(num(r[ix[k]]) for r in data) / max(tot_samp, 1))
-                                                 for k in sorted(st, key=lambda k: -sum(num(r[ix[k]]) for r in data))[:8]))
-    blk = 32
-    for b in range(0, len(data), blk):
-        seg = data[b:b + blk]
-        inst = sum(num(r[ix['Instructions Executed']]) for r in seg); th = sum(num(r[ix['Thread Instructions Executed']]) for r in seg)
-        samp = sum(num(r[ix['# Samples']]) for r in seg)
-        if inst / max(tot_inst, 1) < 0.004:
-            continue
-        stalls = {k: sum(num(r[ix[k]]) for r in seg) for k in st}
-        top = sorted(stalls.items(), key=lambda kv: -kv[1])[:3]
-        ops = ' '.join(sorted(set(r[ix['Source']].split()[0] for r in seg if r[ix['Source']])))
-        print('%4d-%4d inst %5.1f%% thr/inst %5.1f samp %5.1f%% %s | %s' % (b, b + blk, 100 * inst / tot_inst, th / max(inst, 1), 100 * samp / max(tot_samp, 1),
-                                                                           ' '.join('%s=%.0f%%' % (k[6:], 100 * v / max(samp, 1)) for k, v in top), ops[:90]))
+    allrows = list(csv.reader(open(sass)))
+    sections, cur = [], None
+    for r in allrows:
+        if r and r[0] == 'Kernel Name':
+            cur = {'name': r[1] if len(r) > 1 else '?', 'rows': []}; sections.append(cur)
+        elif cur is not None:
+            cur['rows'].append(r)
+    for sec in sections:
+        rows = sec['rows']
+        hdr = rows[0]; ix = {k: i for i, k in enumerate(hdr)}
+        data = [r for r in rows[1:] if len(r) == len(hdr)]
+        print('=' * 100)
+        print('SASS profile of', sec['name'][:120])
+        tot_inst = sum(num(r[ix['Instructions Executed']]) for r in data); tot_samp = sum(num(r[ix['# Samples']]) for r in data)
+        st = [k for k in hdr if k.startswith('stall_') and 'Not Issued' not in k]
+        print('total warp inst %.4g, samples %d' % (tot_inst, tot_samp))
+        print('stall mix (all samples): ' + ' '.join('%s=%.1f%%' % (k[6:], 100 * sum(num(r[ix[k]]) for r in data) / max(tot_samp, 1))
+                                                     for k in sorted(st, key=lambda k: -sum(num(r[ix[k]]) for r in data))[:8]))
+        blk = 32
+        for b in range(0, len(data), blk):
+            seg = data[b:b + blk]
+            inst = sum(num(r[ix['Instructions Executed']]) for r in seg); th = sum(num(r[ix['Thread Instructions Executed']]) for r in seg)
+            samp = sum(num(r[ix['# Samples']]) for r in seg)
+            if inst / max(tot_inst, 1) < 0.004:
+                continue
+            stalls = {k: sum(num(r[ix[k]]) for r in seg) for k in st}
+            top = sorted(stalls.items(), key=lambda kv: -kv[1])[:3]
+            ops = ' '.join(sorted(set(r[ix['Source']].split()[0] for r in seg if r[ix['Source']])))
+            print('%4d-%4d inst %5.1f%% thr/inst %5.1f samp %5.1f%% %s | %s' % (b, b + blk, 100 * inst / tot_inst, th / max(inst, 1), 100 * samp / max(tot_samp, 1),
+                                                                               ' '.join('%s=%.0f%%' % (k[6:], 100 * v / max(samp, 1)) for k, v in top), ops[:90]))
