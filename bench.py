@@ -36,14 +36,14 @@ UNIT = 'path samples/s'
 def workload(rank, world):
     from nlos_surface_optimization_b200 import scenes
     v, f = scenes.bunny()
-    # (64*world) x 64 wall on [-.25,.25]^2; rank r owns rows [64 r, 64 (r+1)) -> contiguous global source indices
+    # (64*world) x 64 wall on [-.25,.25]^2; rank r owns the interleaved rows r, r+world, ... (every rank sees the whole
+    # wall extent => equal work per rank); global source index = rank*L + local index (RNG key, nlos_ctx_set_source_window)
     lin_x = np.linspace(-.25, .25, WALL)
-    lin_y = np.linspace(-.25, .25, WALL * world)
+    lin_y = np.linspace(-.25, .25, WALL * world)[rank::world]
     gx, gy = np.meshgrid(lin_x, lin_y)
-    o = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1).astype(np.float32)
-    L_global = o.shape[0]
-    L = L_global // world
-    o = np.ascontiguousarray(o[rank * L:(rank + 1) * L])
+    o = np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1).astype(np.float32))
+    L = o.shape[0]
+    L_global = L * world
     n = np.ascontiguousarray(np.tile(np.array([0, 0, 1], dtype=np.float32), (L, 1)))
     return o, n, v, f, L, L_global
 
@@ -133,12 +133,10 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def fp32_peak_tflops(torch, dev):
+def fp32_peak_tflops(torch, dev, cx):
     """Measured FP32 FMA throughput (the denominator of the FP32 roofline): a torch elementwise FMA chain is not a
     pure-pipe benchmark, so use the library's own micro-kernel when present; else the nominal 148 SM x 128 lanes x 2 x clock."""
     try:
-        import nlos_surface_optimization_b200 as nb
-        cx = nb.default_context(dev.index)
         v = float(cx.lib.nlos_microbench_fp32(cx.handle))
         if v > 0:
             return v, 'measured here (in-repo FFMA chain, csrc/microbench.cu)'
@@ -174,6 +172,20 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     ctx = nb.Context(local)                       # fails loudly without the CUDA library / a B200
+    try:
+        line = run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local)
+    finally:
+        # ordered teardown: every tensor that lives on the context's stream must be gone before the stream is destroyed
+        import gc
+        gc.collect(); torch.cuda.synchronize(); torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        ctx.close()
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local):
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     o, n, v, f, L, L_global = workload(rank, world)
@@ -292,7 +304,7 @@ def main():
         flops_fwd_sample = 32 + 23 * box + 50 * tri + rho * 48
         fwd_ms = phase['forward_ms']
         achieved = L * F * spp * flops_fwd_sample / (fwd_ms * 1e-3) / 1e12
-        peak, peak_how = fp32_peak_tflops(torch, dev)
+        peak, peak_how = fp32_peak_tflops(torch, dev, ctx)
         try:
             red_peak = float(ctx.lib.nlos_microbench_red_f64(ctx.handle, L * B))       # FP64 RED.ADD over the transient's address range
         except Exception:
@@ -318,9 +330,8 @@ def main():
         }
         if cpu:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 if __name__ == '__main__':
