@@ -161,7 +161,7 @@ __global__ void k_emit_nodes(int F, const int2* __restrict__ child, const int* _
   n.a = make_float4(lo[0].x, lo[0].y, lo[0].z, hi[0].x);
   n.b = make_float4(hi[0].y, hi[0].z, lo[1].x, lo[1].y);
   n.c = make_float4(lo[1].z, hi[1].x, hi[1].y, hi[1].z);
-  n.d = make_int4(link[0], link[1], cnt[0], cnt[1]);
+  n.d = make_int4(cnt[0] > 0 ? leaf_ref(link[0], cnt[0]) : link[0], cnt[1] > 0 ? leaf_ref(link[1], cnt[1]) : link[1], 0, 0);
   nodes[i] = n;
 }
 

@@ -110,10 +110,13 @@ NLOS_HD bool isect(const TriRec& tr, f3 o, f3 d, float& t, float& u, float& v) {
 
 // ------------------------------------------------------------------ BVH node (64 B): two child boxes + links
 // a = (lo0.x lo0.y lo0.z hi0.x)  b = (hi0.y hi0.z lo1.x lo1.y)  c = (lo1.z hi1.x hi1.y hi1.z)
-// d = (child0, child1, count0, count1); count>0 => child is the first sorted triangle of a leaf run
+// d = (ref0, ref1, -, -): ref >= 0 is an internal node index, ref < 0 encodes a leaf run ~((first << 3) | (count-1))
 struct BvhNode { float4 a, b, c; int4 d; };
+NLOS_HD int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
+NLOS_HD int leaf_first(int ref) { return (~ref) >> 3; }
+NLOS_HD int leaf_count(int ref) { return ((~ref) & 7) + 1; }
 
-constexpr int kLeafMax = 4;      // a subtree with <= kLeafMax triangles is tested linearly
+constexpr int kLeafMax = 4;      // a subtree with <= kLeafMax (<= 8) triangles is tested linearly
 constexpr int kStack = 64;       // >= depth of a 62-bit-key LBVH
 
 NLOS_HD float safe_rcp(float x) {
@@ -184,8 +187,8 @@ NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restric
     bool h0 = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
     bool h1 = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
     if (n_box) *n_box += 2;
-    if (h0 && d.z > 0) { for (int j = 0; j < d.z; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, d.x + j, r, t_self, prim_self)) return true; } h0 = false; }
-    if (h1 && d.w > 0) { for (int j = 0; j < d.w; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, d.y + j, r, t_self, prim_self)) return true; } h1 = false; }
+    if (h0 && d.x < 0) { const int f0 = leaf_first(d.x), c0 = leaf_count(d.x); for (int j = 0; j < c0; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, f0 + j, r, t_self, prim_self)) return true; } h0 = false; }
+    if (h1 && d.y < 0) { const int f1 = leaf_first(d.y), c1 = leaf_count(d.y); for (int j = 0; j < c1; ++j) { if (n_tri) ++*n_tri; if (tri_occludes(ttris, f1 + j, r, t_self, prim_self)) return true; } h1 = false; }
     if (h0 && h1) {
       const bool first0 = t0 <= t1;
       stack[sp++] = first0 ? d.y : d.x; node = first0 ? d.x : d.y;
@@ -199,13 +202,12 @@ NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restric
 // run (or is done), then all lanes test their leaf triangles together — the warp executes box tests with box tests and
 // triangle tests with triangle tests instead of interleaving them per lane.  Same answer as occluded().
 constexpr int kSentinel = 0x7fffffff;
-NLOS_HD int child_ref(int link, int cnt) { return cnt > 0 ? ~((link << 2) | (cnt - 1)) : link; }   // leaf run -> negative
 
 NLOS_HD bool occluded_ww(const BvhNode* __restrict__ nodes, const float4* __restrict__ ttris, int root_count,
                          const Ray& r, float t_self, int prim_self) {
   const float tlim = t_self * 1.000001f;
   int stack[kStack]; int sp = 0;
-  int cur = root_count > 0 ? child_ref(0, root_count) : 0;
+  int cur = root_count > 0 ? leaf_ref(0, root_count) : 0;
   while (cur != kSentinel) {
     while ((unsigned)cur < (unsigned)kSentinel) {                    // internal node
       const float4 a = NLOS_LDG4(&nodes[cur].a), b = NLOS_LDG4(&nodes[cur].b), c = NLOS_LDG4(&nodes[cur].c);
@@ -213,7 +215,7 @@ NLOS_HD bool occluded_ww(const BvhNode* __restrict__ nodes, const float4* __rest
       float t0, t1;
       const bool h0 = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
       const bool h1 = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
-      const int r0 = child_ref(d.x, d.z), r1 = child_ref(d.y, d.w);
+      const int r0 = d.x, r1 = d.y;
       if (h0 && h1) {
         const bool first0 = t0 <= t1;
         stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1;
@@ -222,7 +224,7 @@ NLOS_HD bool occluded_ww(const BvhNode* __restrict__ nodes, const float4* __rest
       else cur = sp ? stack[--sp] : kSentinel;
     }
     while (cur < 0) {                                                // leaf run of 1..4 triangles
-      const int enc = ~cur; const int first = enc >> 2, cnt = (enc & 3) + 1;
+      const int first = leaf_first(cur), cnt = leaf_count(cur);
       for (int j = 0; j < cnt; ++j) if (tri_occludes(ttris, first + j, r, t_self, prim_self)) return true;
       cur = sp ? stack[--sp] : kSentinel;
     }

@@ -42,7 +42,7 @@ struct SahBuilder {
     else { float ext = chi[bestAx]-clo[bestAx]; auto it = std::partition(order.begin()+a, order.begin()+b, [&](int t){ const f3& c = cen[t]; float v = bestAx==0?c.x:(bestAx==1?c.y:c.z); int bi = std::min(NB-1,(int)((v-clo[bestAx])/ext*NB)); return bi<=bestSplit;}); mid = (int)(it-order.begin()); if (mid==a||mid==b) mid=(a+b)/2; }
     int id = (int)nodes.size(); nodes.push_back(BvhNode());
     int l0,c0,l1,c1; B6 b0,b1; build(a, mid, l0,c0,b0); build(mid, b, l1,c1,b1);
-    BvhNode n; n.a = make_float4(b0.lo[0],b0.lo[1],b0.lo[2],b0.hi[0]); n.b = make_float4(b0.hi[1],b0.hi[2],b1.lo[0],b1.lo[1]); n.c = make_float4(b1.lo[2],b1.hi[0],b1.hi[1],b1.hi[2]); n.d = make_int4(l0,l1,c0,c1);
+    BvhNode n; n.a = make_float4(b0.lo[0],b0.lo[1],b0.lo[2],b0.hi[0]); n.b = make_float4(b0.hi[1],b0.hi[2],b1.lo[0],b1.lo[1]); n.c = make_float4(b1.lo[2],b1.hi[0],b1.hi[1],b1.hi[2]); n.d = make_int4(c0>0?leaf_ref(l0,c0):l0, c1>0?leaf_ref(l1,c1):l1, 0, 0);
     nodes[id] = n; link = id; cnt = 0;
   }
 };
@@ -71,7 +71,7 @@ int bvh_quality(const float* origin, int L, const float* verts, int V, const int
     nodes.resize(NI);
     for (int i=0;i<NI;++i){int link[2],cnt[2];B6 bx[2];int cc[2]={cl[i],cr[i]};
       for(int k=0;k<2;++k){int c=cc[k]; if(c<0){link[k]=~c;cnt[k]=1;bx[k]=leaf[order[~c]];} else {int size=last[c]-first[c]+1;bx[k]=nb[c]; if(size<=leafmax){link[k]=first[c];cnt[k]=size;} else {link[k]=c;cnt[k]=0;}}}
-      BvhNode n; n.a=make_float4(bx[0].lo[0],bx[0].lo[1],bx[0].lo[2],bx[0].hi[0]); n.b=make_float4(bx[0].hi[1],bx[0].hi[2],bx[1].lo[0],bx[1].lo[1]); n.c=make_float4(bx[1].lo[2],bx[1].hi[0],bx[1].hi[1],bx[1].hi[2]); n.d=make_int4(link[0],link[1],cnt[0],cnt[1]); nodes[i]=n;}
+      BvhNode n; n.a=make_float4(bx[0].lo[0],bx[0].lo[1],bx[0].lo[2],bx[0].hi[0]); n.b=make_float4(bx[0].hi[1],bx[0].hi[2],bx[1].lo[0],bx[1].lo[1]); n.c=make_float4(bx[1].lo[2],bx[1].hi[0],bx[1].hi[1],bx[1].hi[2]); n.d=make_int4(cnt[0]>0?leaf_ref(link[0],cnt[0]):link[0], cnt[1]>0?leaf_ref(link[1],cnt[1]):link[1],0,0); nodes[i]=n;}
   }
   std::vector<float4> ttris(4*(size_t)F), stris(4*(size_t)F);
   for (int p=0;p<F;++p){int f=order[p]; f3 v1=ldv(verts,faces[3*f]),v2=ldv(verts,faces[3*f+1]),v3=ldv(verts,faces[3*f+2]); TriRec tr=make_tri(v1,v2,v3);

@@ -91,7 +91,7 @@ static void build(const float* verts, int V, const int* faces, int F, const floa
     n.a = make_float4(bx[0].lo[0], bx[0].lo[1], bx[0].lo[2], bx[0].hi[0]);
     n.b = make_float4(bx[0].hi[1], bx[0].hi[2], bx[1].lo[0], bx[1].lo[1]);
     n.c = make_float4(bx[1].lo[2], bx[1].hi[0], bx[1].hi[1], bx[1].hi[2]);
-    n.d = make_int4(link[0], link[1], cnt[0], cnt[1]);
+    n.d = make_int4(cnt[0] > 0 ? leaf_ref(link[0], cnt[0]) : link[0], cnt[1] > 0 ? leaf_ref(link[1], cnt[1]) : link[1], 0, 0);
     out.nodes[i] = n;
   }
 }

@@ -19,12 +19,14 @@ def _scene(name):
         v, f = scenes.icosphere(4, 0.1, (0.02, -0.03, 0.45), noise=0.03, seed=3); o, n = scenes.wall_grid(6); ns = 20000
     elif name == 'bunny':
         v, f = scenes.bunny(); o, n = scenes.wall_grid(4); ns = 20000
+    elif name == 'heightfield':        # the C-scale mesh family at test size (self-shadowing ridges, open surface)
+        v, f = scenes.heightfield(41); o, n = scenes.wall_grid(5); ns = 3 * f.shape[0]
     else:
         raise KeyError(name)
     return o, n, v, f, ns
 
 
-@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny'])
+@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny', 'heightfield'])
 def test_visibility_bit_exact(name, oracle, gpu_ctx):
     import nlos_surface_optimization_b200 as nb
     o, n, v, f, ns = _scene(name)
@@ -52,7 +54,7 @@ def test_forward_transient(name, refine, sigma, oracle, gpu_ctx):
         assert np.array_equal(T > 0, T_ref > 0)
 
 
-@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny'])
+@pytest.mark.parametrize('name', ['fan8', 'occluders', 'ico', 'bunny', 'heightfield'])
 def test_vertex_gradient(name, oracle, gpu_ctx):
     from nlos_surface_optimization_b200 import renderer
     o, n, v, f, ns = _scene(name)

@@ -1,0 +1,28 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import numpy as np
+import nlos_surface_optimization_b200 as nb
+from nlos_surface_optimization_b200 import renderer, ggx, scenes
+ctx = nb.Context(0)
+o, n = scenes.wall_grid(3)
+v, f = scenes.icosphere(2, 0.1, (0.01, -0.02, 0.45), noise=0.03, seed=1)
+vn = scenes.vertex_normals(v, f); alb = np.ones(v.shape[0], np.float32)
+ns, lb, ub, res, B = 3 * f.shape[0], 0.0, 1.44, 1.2e-3, 1200
+L, V = o.shape[0], v.shape[0]
+T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((V, 3)); data = np.zeros((L, B)); w = np.ones((L, B))
+renderer.renderStreamedTransient(o, n, v, f, ns, lb, ub, res, data, pl, 1, 1, ctx=ctx)
+renderer.renderStreamedTransient(o, n, v, f, ns, lb, ub, res, T, pl, 10, 1, ctx=ctx)
+renderer.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 1, 0, ctx=ctx)
+renderer.renderStreamedShadingGradient(o, n, v, f, vn, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 0, 0, ctx=ctx)
+renderer.renderStreamedGradientWithAlbedo(o, n, v, f, alb, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 1, 0, ctx=ctx)
+renderer.renderStreamedGradientAlbedo(o, n, v, f, alb, ns, lb, ub, res, T, pl, data, w, 10, 1, 1, 0, ctx=ctx)
+ggx.renderStreamedGradient(o, n, v, f, 0.3, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 1, ctx=ctx)
+ggx.renderStreamedGradientAlpha(o, n, v, f, 0.3, ns, lb, ub, res, T, pl, data, w, 10, 1, ctx=ctx)
+I = np.zeros(f.shape[0]); renderer.renderStreamedTriangleIntensity(o, n, v, f, ns, lb, ub, I, ctx=ctx)
+Gb = np.zeros((B, 3)); renderer.renderStreamedVertexGradient(o, n, v, f, ns, lb, ub, res, Gb, 5, 10, 1, ctx=ctx)
+renderer.renderStreamedNormalSmoothing(v, f, scenes.face_affinity(f), G, ctx=ctx); renderer.renderStreamedCurvatureGradient(v, f, G, ctx=ctx)
+ctx.set_option('reuse_visibility', 0)
+renderer.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 1, 0, ctx=ctx)
+vis, cnt = nb.debug_visibility(o, v, f, ns, ctx=ctx)
+print('sanitize run ok', T.sum(), np.abs(G).sum(), vis.mean())
