@@ -153,6 +153,22 @@ int nlos_ggx_streamed_render_gradient_alpha(nlos_ctx* ctx, const double* data, c
                                             float pathlengthResolution, double* transient, double* pathlengths,
                                             int refine_scale, int sigma_bin, int numBins, double* result /*host*/);
 
+/* ---- module `embree_intersector` (embree_intersector/), SURVEY.md 8f row N2 ---------------------------- */
+
+/* embree_intersector/c_embree_intersector.h:8  embree3_tbb_line_intersection (embree_intersector.pyx:92):
+ * nearest hit per ray, intersect[3i..3i+2] = (primID, u, v) as floats, or intersect[3i] = -1 (u,v untouched) */
+int nlos_embree3_tbb_line_intersection(nlos_ctx* ctx, const float* originsD, const float* directionsD, int num_ray,
+                                       const float* verticesD, int num_vertices, const int* trianglesD, int num_triangles,
+                                       float* intersect);
+/* c_embree_intersector.h:9  embree3_tbb_short_line_intersection (embree_intersector.pyx:81): intersect[i] = primID or -1 */
+int nlos_embree3_tbb_short_line_intersection(nlos_ctx* ctx, const float* originsD, const float* directionsD, int num_ray,
+                                             const float* verticesD, int num_vertices, const int* trianglesD,
+                                             int num_triangles, float* intersect);
+/* c_embree_intersector.h:4  barycentric_to_world (embree_intersector.pyx:69); the two mesh sizes are additions
+ * (needed to stage host arrays); rows with primID < 0 are left untouched */
+int nlos_barycentric_to_world(nlos_ctx* ctx, const float* verticesD, int num_vertices, const int* trianglesD, int num_triangles,
+                              const float* barycoord, int num_ray, float* intersection_p);
+
 /* ---- test / profiling hooks ------------------------------------------------------------------------ */
 
 /* Pure-geometry per-sample visibility (nearest hit == sampled triangle, TG.cpp:206) as bytes [L,F,spp];

@@ -106,7 +106,47 @@ __global__ void k_regulariser(const float* __restrict__ verts, const int* __rest
   }
 }
 
+// ---- embree_intersector API: batched nearest-hit queries on the same LBVH
+// MODE 0: intersect[3i..] = (primID, u, v) or intersect[3i] = -1 (c_embree_intersector.cpp:20-46);  MODE 1: intersect[i] = primID or -1 (:49-75)
+template <int MODE>
+__global__ void k_ray_query(const DeviceScene sc, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t N, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const f3 o = mk3(__ldg(origins + 3 * i), __ldg(origins + 3 * i + 1), __ldg(origins + 3 * i + 2));
+    const f3 d = mk3(__ldg(dirs + 3 * i), __ldg(dirs + 3 * i + 1), __ldg(dirs + 3 * i + 2));
+    const Ray ray = make_ray(o, d);
+    const HitRec h = nearest_hit(sc.nodes, sc.ttris, sc.root_count, ray);
+    if (MODE == 1) out[i] = h.prim < 0 ? -1.0f : (float)h.prim;
+    else if (h.prim < 0) out[3 * i] = -1.0f;
+    else { out[3 * i] = (float)h.prim; out[3 * i + 1] = h.u; out[3 * i + 2] = h.v; }
+  }
+}
+// c_embree_intersector.cpp:77-96 coord_conversion
+__global__ void k_bary_to_world(const float* __restrict__ verts, const int* __restrict__ faces, const float* __restrict__ bary, int64_t N, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int fid = (int)bary[3 * i];
+    if (fid < 0) continue;
+    const float u = bary[3 * i + 1], v = bary[3 * i + 2];
+    const int v1 = faces[3 * (size_t)fid], v2 = faces[3 * (size_t)fid + 1], v3 = faces[3 * (size_t)fid + 2];
+    for (int k = 0; k < 3; ++k) out[3 * i + k] = (1 - u - v) * verts[3 * (size_t)v1 + k] + u * verts[3 * (size_t)v2 + k] + v * verts[3 * (size_t)v3 + k];
+  }
+}
+
 }  // namespace
+
+void launch_ray_query(Ctx& cx, const DeviceScene& sc, int mode, const float* origins, const float* dirs, int64_t N, float* out) {
+  if (N <= 0) return;
+  const int blocks = (int)std::min<int64_t>((N + 127) / 128, 148 * 32);
+  if (mode == 1) k_ray_query<1><<<blocks, 128, 0, cx.stream>>>(sc, origins, dirs, N, out);
+  else k_ray_query<0><<<blocks, 128, 0, cx.stream>>>(sc, origins, dirs, N, out);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
+void launch_bary_to_world(Ctx& cx, const float* verts, const int* faces, const float* bary, int64_t N, float* out) {
+  if (N <= 0) return;
+  k_bary_to_world<<<(int)std::min<int64_t>((N + 255) / 256, 148 * 16), 256, 0, cx.stream>>>(verts, faces, bary, N, out);
+  cx.launches += 1;
+  NLOS_CUDA_OK(cudaGetLastError());
+}
 
 void launch_vertex_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, int vertex_num, const double* taps, double sigma2, double* acc) {
   if (sc.F <= 0 || P.L <= 0) return;

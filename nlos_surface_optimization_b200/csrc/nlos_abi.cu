@@ -483,6 +483,61 @@ int nlos_streamed_render_curvature_grad(nlos_ctx* ctx, const float* verticesD, i
   return run_regulariser(ctx, 1, verticesD, numVertices, trianglesD, numTriangles, nullptr, curvature_grad, nullptr);
 }
 
+static int run_ray_query(nlos_ctx* ctx, int mode, const float* originsD, const float* directionsD, int num_ray, const float* verticesD, int num_vertices,
+                         const int* trianglesD, int num_triangles, float* intersect) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_REQUIRE(num_ray >= 0 && num_vertices > 0 && num_triangles > 0, "bad size");
+    if (num_ray == 0) return NLOS_OK;
+    NLOS_REQUIRE(originsD && directionsD && verticesD && trianglesD && intersect, "null argument");
+    cudaStream_t st = cx.stream;
+    const int64_t N = num_ray;
+    const float* d_o = stage_in(cx, "in_origin", originsD, 3 * (size_t)N, st);
+    const float* d_d = stage_in(cx, "in_dirs", directionsD, 3 * (size_t)N, st);
+    const float* d_verts = stage_in(cx, "in_verts", verticesD, 3 * (size_t)num_vertices, st);
+    const int* d_faces = stage_in(cx, "in_faces", trianglesD, 3 * (size_t)num_triangles, st);
+    OutView<float> o_out = stage_out(cx, "out_isect", intersect, (mode == 1 ? 1 : 3) * (size_t)N, mode == 0);   // misses leave (u,v) untouched
+    DeviceScene sc; build_scene(cx, d_verts, num_vertices, d_faces, num_triangles, d_o, N, nullptr, nullptr, sc);
+    launch_ray_query(cx, sc, mode, d_o, d_d, N, o_out.dev);
+    if (finish_out(cx, o_out)) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    cx.last_error.clear();
+    return NLOS_OK;
+  } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
+  catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
+int nlos_embree3_tbb_line_intersection(nlos_ctx* ctx, const float* originsD, const float* directionsD, int num_ray, const float* verticesD, int num_vertices,
+                                       const int* trianglesD, int num_triangles, float* intersect) {
+  return run_ray_query(ctx, 0, originsD, directionsD, num_ray, verticesD, num_vertices, trianglesD, num_triangles, intersect);
+}
+int nlos_embree3_tbb_short_line_intersection(nlos_ctx* ctx, const float* originsD, const float* directionsD, int num_ray, const float* verticesD,
+                                             int num_vertices, const int* trianglesD, int num_triangles, float* intersect) {
+  return run_ray_query(ctx, 1, originsD, directionsD, num_ray, verticesD, num_vertices, trianglesD, num_triangles, intersect);
+}
+int nlos_barycentric_to_world(nlos_ctx* ctx, const float* verticesD, int num_vertices, const int* trianglesD, int num_triangles, const float* barycoord,
+                              int num_ray, float* intersection_p) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_REQUIRE(num_ray >= 0 && num_vertices > 0 && num_triangles > 0, "bad size");
+    if (num_ray == 0) return NLOS_OK;
+    NLOS_REQUIRE(verticesD && trianglesD && barycoord && intersection_p, "null argument");
+    cudaStream_t st = cx.stream;
+    const float* d_verts = stage_in(cx, "in_verts", verticesD, 3 * (size_t)num_vertices, st);
+    const int* d_faces = stage_in(cx, "in_faces", trianglesD, 3 * (size_t)num_triangles, st);
+    const float* d_b = stage_in(cx, "in_bary", barycoord, 3 * (size_t)num_ray, st);
+    OutView<float> o_out = stage_out(cx, "out_world", intersection_p, 3 * (size_t)num_ray, true);   // misses stay untouched
+    launch_bary_to_world(cx, d_verts, d_faces, d_b, num_ray, o_out.dev);
+    if (finish_out(cx, o_out)) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    cx.last_error.clear();
+    return NLOS_OK;
+  } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
+  catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
 int nlos_debug_visibility(nlos_ctx* ctx, const float* originD, int numSources, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles,
                           int numSamples, uint8_t* visibility, uint64_t* counters3) {
   if (!ctx) return NLOS_ERR_INVALID;

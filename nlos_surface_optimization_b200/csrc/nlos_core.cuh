@@ -198,6 +198,46 @@ NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restric
   }
 }
 
+// Nearest hit over the whole mesh: lexicographic minimum of (t, primitive index) over all float-valid intersections —
+// the restatement of rtcIntersect1 used by the embree_intersector API (embree_intersector/c_embree_intersector.cpp:20-46).
+struct HitRec { int prim; float t, u, v; };
+NLOS_HD void hit_run(const float4* __restrict__ ttris, int first, int cnt, const Ray& r, HitRec& best) {
+  for (int j = 0; j < cnt; ++j) {
+    float4 q0, q1, q2, q3;
+    ld256(ttris + 4 * (size_t)(first + j), q0, q1);
+    ld256(ttris + 4 * (size_t)(first + j) + 2, q2, q3);
+    TriRec tr; tr.v0 = xyz(q0); tr.e1 = xyz(q1); tr.e2 = xyz(q2); tr.Ng = xyz(q3);
+    float t, u, v;
+    if (!isect(tr, r.o, r.d, t, u, v)) continue;
+    const int prim = f2i(q0.w);
+    if (t < best.t || (t == best.t && prim < best.prim)) { best.prim = prim; best.t = t; best.u = u; best.v = v; }
+  }
+}
+NLOS_HD HitRec nearest_hit(const BvhNode* __restrict__ nodes, const float4* __restrict__ ttris, int root_count, const Ray& r) {
+  HitRec best; best.prim = -1; best.t = 3.0e38f; best.u = best.v = 0.f;
+  if (root_count > 0) { hit_run(ttris, 0, root_count, r, best); return best; }
+  int stack[kStack]; int sp = 0; int node = 0;
+  while (true) {
+    const float4 a = NLOS_LDG4(&nodes[node].a), b = NLOS_LDG4(&nodes[node].b), c = NLOS_LDG4(&nodes[node].c);
+    const int4 d = *reinterpret_cast<const int4*>(&nodes[node].d);
+    const float tlim = best.t * 1.000001f;
+    float t0, t1;
+    bool h0 = slab(r, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
+    bool h1 = slab(r, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
+    if (h0 && d.x < 0) { hit_run(ttris, leaf_first(d.x), leaf_count(d.x), r, best); h0 = false; }
+    if (h1 && d.y < 0) { hit_run(ttris, leaf_first(d.y), leaf_count(d.y), r, best); h1 = false; }
+    if (h0 && h1) { const bool first0 = t0 <= t1; stack[sp++] = first0 ? d.y : d.x; node = first0 ? d.x : d.y; }
+    else if (h0) node = d.x;
+    else if (h1) node = d.y;
+    else {
+      // nodes pushed earlier may have become farther than the best hit found since: re-test on pop is not needed for
+      // correctness (their triangles simply lose), only costs time
+      if (sp == 0) return best;
+      node = stack[--sp];
+    }
+  }
+}
+
 // "while-while" variant used by the hot forward kernel: every lane first walks internal nodes until it holds a leaf
 // run (or is done), then all lanes test their leaf triangles together — the warp executes box tests with box tests and
 // triangle tests with triangle tests instead of interleaving them per lane.  Same answer as occluded().

@@ -15,6 +15,8 @@ void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n);
 void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res);
 // mesh_kernels.cu
 void launch_vertex_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, int vertex_num, const double* taps, double sigma2, double* acc);
+void launch_ray_query(Ctx& cx, const DeviceScene& sc, int mode, const float* origins, const float* dirs, int64_t N, float* out);
+void launch_bary_to_world(Ctx& cx, const float* verts, const int* faces, const float* bary, int64_t N, float* out);
 void launch_regulariser(Ctx& cx, int mode, const float* verts, int V, const int* faces, int F, const int* aff, double* grad, double* value);
 
 }  // namespace nlos

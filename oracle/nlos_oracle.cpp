@@ -677,6 +677,27 @@ void nlos_oracle_curvature_grad(const float* verts, int V, const int32_t* faces,
   }
 }
 
+
+// embree_intersector/c_embree_intersector.cpp:20-96 — batched nearest hit (primID,u,v) / primID, and barycentric -> world
+int nlos_oracle_intersect(const float* origins, const float* dirs, int64_t N, const float* verts, int V, const int32_t* faces, int F, float* out3, float* out1, int mode) {
+  Scene sc; build_scene(sc, verts, V, faces, F, origins, N, mode & 1);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < N; ++i) {
+    Hit h = nearest_hit(sc, ld3(origins, i), ld3(dirs, i), nullptr);
+    if (out1) out1[i] = h.prim < 0 ? -1.0f : (float)h.prim;
+    if (out3) { if (h.prim < 0) out3[3 * i] = -1.0f; else { out3[3 * i] = (float)h.prim; out3[3 * i + 1] = h.u; out3[3 * i + 2] = h.v; } }
+  }
+  return 0;
+}
+void nlos_oracle_bary_to_world(const float* verts, const int32_t* faces, const float* bary, int64_t N, float* out) {
+  for (int64_t i = 0; i < N; ++i) {
+    int fid = (int)bary[3 * i]; if (fid < 0) continue;
+    float u = bary[3 * i + 1], v = bary[3 * i + 2];
+    int v1 = faces[3 * fid], v2 = faces[3 * fid + 1], v3 = faces[3 * fid + 2];
+    for (int k = 0; k < 3; ++k) out[3 * i + k] = (1 - u - v) * verts[3 * v1 + k] + u * verts[3 * v2 + k] + v * verts[3 * v3 + k];
+  }
+}
+
 // helpers exported for unit tests
 void nlos_oracle_philox(uint64_t seed, int64_t src, int tri, int k, float* S, float* T) { sample_ST(seed, src, tri, k, *S, *T); }
 int nlos_oracle_isect(const float* v /*9*/, const float* o, const float* d, float* tuv) {

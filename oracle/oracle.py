@@ -177,3 +177,20 @@ def taps(res, r, s):
 
 def threads():
     return lib().nlos_oracle_threads()
+
+
+def intersect(origin, direction, vertices, faces, brute=False):
+    """nearest hit per ray -> (barycoord[N,3] f32 = (primID,u,v) or (-1,0,0), prim[N] f32)"""
+    origin = _f32(origin); direction = _f32(direction); vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    N = origin.shape[0]
+    out3 = np.zeros((N, 3), dtype=np.float32); out1 = np.zeros(N, dtype=np.float32)
+    lib().nlos_oracle_intersect(_p(origin, C.c_float), _p(direction, C.c_float), C.c_int64(N), _p(vertices, C.c_float), C.c_int(vertices.shape[0]),
+                                _p(faces, C.c_int32), C.c_int(faces.shape[0]), _p(out3, C.c_float), _p(out1, C.c_float), C.c_int(1 if brute else 0))
+    return out3, out1
+
+
+def bary_to_world(vertices, faces, bary):
+    vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32); bary = _f32(bary)
+    out = np.zeros((bary.shape[0], 3), dtype=np.float32)
+    lib().nlos_oracle_bary_to_world(_p(vertices, C.c_float), _p(faces, C.c_int32), _p(bary, C.c_float), C.c_int64(bary.shape[0]), _p(out, C.c_float))
+    return out

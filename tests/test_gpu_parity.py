@@ -327,3 +327,30 @@ def test_vertex_gradient_debug_and_regularisers(oracle, gpu_ctx):
         Gc = np.full((mv.shape[0], 3), 5.0)
         renderer.renderStreamedCurvatureGradient(mv, mf, Gc, ctx=gpu_ctx)
         assert np.array_equal(Gc, C_ref)
+
+
+def test_embree_intersector_api(oracle, gpu_ctx):
+    """batched nearest-hit queries (primID,u,v) on the renderer's LBVH equal the oracle's nearest hit exactly."""
+    from nlos_surface_optimization_b200 import embree_intersector as ei, scenes
+    rng = np.random.RandomState(5)
+    for v, f in (scenes.icosphere(4, 0.1, (0, 0, 0.45), noise=0.04, seed=2), scenes.bunny()):
+        N = 20000
+        o = np.ascontiguousarray(np.stack([rng.uniform(-.25, .25, N), rng.uniform(-.25, .25, N), np.zeros(N)], 1), dtype=np.float32)
+        tgt = v[rng.randint(0, v.shape[0], N)] + rng.normal(0, 0.01, (N, 3))
+        d = np.ascontiguousarray((tgt - o) * rng.uniform(0.5, 2.0, (N, 1)), dtype=np.float32)      # not normalised on purpose
+        ref3, ref1 = oracle.intersect(o, d, v, f)
+        b3 = np.full((N, 3), 7.0, dtype=np.float32); b1 = np.zeros(N, dtype=np.float32)
+        ei.embree3_tbb_intersection(o, d, v, f, b3, ctx=gpu_ctx)
+        ei.embree3_tbb_short_intersection(o, d, v, f, b1, ctx=gpu_ctx)
+        hit = ref1 >= 0
+        assert 0.2 < hit.mean() < 1.0
+        assert np.array_equal(b1, ref1)
+        assert np.array_equal(b3[hit], ref3[hit])
+        assert np.array_equal(b3[~hit, 0], ref3[~hit, 0]) and (b3[~hit, 1:] == 7.0).all()      # misses leave (u,v) untouched
+        p_ref = oracle.bary_to_world(v, f, ref3)
+        p = np.full((N, 3), 9.0, dtype=np.float32)
+        ei.PyMesh(v, f, ctx=gpu_ctx).barycoord_to_world(b3, p)
+        assert np.array_equal(p[hit], p_ref[hit]) and (p[~hit] == 9.0).all()
+        # the hit point lies on the ray
+        t = np.linalg.norm(p[hit] - o[hit], axis=1) / np.linalg.norm(d[hit], axis=1)
+        assert np.abs(o[hit] + t[:, None] * d[hit] - p[hit]).max() < 1e-4

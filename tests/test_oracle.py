@@ -333,3 +333,20 @@ def test_golden_fixtures_pin_the_oracle(oracle):
     for row, ref in zip(gb['rows'][:2], gb['transient_rows'][:2]):
         Tr = oracle.transient(bo[row:row + 1], bn[row:row + 1], bv, bf, int(gb['num_sample']), LB, UB, RES, src_offset=int(row))[0]
         assert np.array_equal(Tr[0], ref)
+
+
+def test_ray_query_oracle_bvh_equals_brute_force(oracle):
+    """embree_intersector restatement: nearest hit (primID,u,v) per ray; BVH and brute force agree, hit points lie on the rays."""
+    from nlos_surface_optimization_b200 import scenes
+    v, f = scenes.icosphere(3, 0.1, (0, 0, 0.45), noise=0.05, seed=4)
+    rng = np.random.RandomState(2); N = 3000
+    o = np.stack([rng.uniform(-.25, .25, N), rng.uniform(-.25, .25, N), np.zeros(N)], 1).astype(np.float32)
+    d = ((v[rng.randint(0, v.shape[0], N)] + rng.normal(0, 0.02, (N, 3)) - o) * rng.uniform(0.5, 2, (N, 1))).astype(np.float32)
+    b3, b1 = oracle.intersect(o, d, v, f)
+    c3, c1 = oracle.intersect(o, d, v, f, brute=True)
+    assert np.array_equal(b3, c3) and np.array_equal(b1, c1)
+    hit = b1 >= 0
+    assert 0.3 < hit.mean() < 1
+    p = oracle.bary_to_world(v, f, b3)
+    t = np.linalg.norm(p[hit] - o[hit], axis=1) / np.linalg.norm(d[hit], axis=1)
+    assert np.abs(o[hit] + t[:, None] * d[hit] - p[hit]).max() < 1e-5
