@@ -153,6 +153,25 @@ int nlos_ggx_streamed_render_gradient_alpha(nlos_ctx* ctx, const double* data, c
                                             float pathlengthResolution, double* transient, double* pathlengths,
                                             int refine_scale, int sigma_bin, int numBins, double* result /*host*/);
 
+/* ---- module `jitter` (jitter/), SURVEY.md 8f row N3: tabulated SPAD-jitter temporal kernel --------------------- */
+
+/* jitter/stratifiedStreamedTransientRenderer.h:3  streamed_render_transient (jitter.pyx:140, :104, :122):
+ * T[s,b] = sum_i weight[i] * hist[s, b + weight_offset - i] */
+int nlos_jitter_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                          const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                          const float* vertexAlbedo /*nullable*/, const int* trianglesD, int numTriangles,
+                                          int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                          float pathlengthResolution, const double* weight, int weight_offset,
+                                          int weight_length, double* transient, double* pathlengths, int numBins);
+/* jitter/stratifiedStreamedGradientRenderer.h:9  streamed_render_gradient (jitter.pyx:59) */
+int nlos_jitter_streamed_render_gradient(nlos_ctx* ctx, const double* data, const double* weight, const float* originD,
+                                         int measurement, const float* normalD, const float* verticesD, int numVertices,
+                                         const float* vertexNormal /*nullable*/, const int* trianglesD, int numTriangles,
+                                         int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                         float pathlengthResolution, const double* jitter_weight, const double* jitter_grad,
+                                         int weight_offset, int weight_length, double* transient, double* pathlengths,
+                                         double* gradient, int testing_flag, int numBins);
+
 /* ---- module `embree_intersector` (embree_intersector/), SURVEY.md 8f row N2 ---------------------------- */
 
 /* embree_intersector/c_embree_intersector.h:8  embree3_tbb_line_intersection (embree_intersector.pyx:92):

@@ -97,6 +97,7 @@ struct Job {
   double* transient = nullptr; double* pathlengths = nullptr; double* gradient = nullptr; double* intensity = nullptr;
   double* scalar_out = nullptr;
   int kind = -1;   // -1 forward only, 0 vertex gradient, 1 albedo scalar, 2 alpha scalar, 3 intensity
+  const double* jw = nullptr; const double* jg = nullptr; int joff = 0, jlen = 0;   // jitter/ temporal kernel (jlen > 0)
 };
 
 int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
@@ -169,7 +170,7 @@ void run_job(Ctx& cx, const Job& j) {
     P.lb = j.lb; P.ub = j.ub; P.res = j.res; P.numBins = std::max(j.numBins, 1);
     P.r_grad = j.refine; P.s_bin = j.sigma; P.K = 4 * j.refine * j.sigma + 1;
     P.r_fwd = (j.kind >= 0 && j.kind <= 2) ? (j.sigma < 5 ? 1 : j.refine) : j.refine;   // SSG.cpp:521-524
-    if (j.kind == 3) P.r_fwd = 1;
+    if (j.kind == 3 || j.jlen > 0) P.r_fwd = 1;                                          // jitter: coarse histogram, then tabulated conv
     P.res_fwd = j.res / P.r_fwd;                                                         // TG.cpp:313
     P.alpha = j.alpha; P.testing_flag = j.testing_flag;
     P.words_per_row = (j.F + 31) / 32;
@@ -178,6 +179,7 @@ void run_job(Ctx& cx, const Job& j) {
       taps = make_taps(j.res, j.refine, j.sigma);
       P.inv_res_fine = (double)j.refine / (double)j.res;
       P.two_over_sigma2 = 2.0 / taps.sigma2;
+      P.grad_coef = j.jlen > 0 ? -2.0 / (double)j.res : P.two_over_sigma2;
     }
     double* d_wprefix = nullptr; double* d_dprefix = nullptr;
     if (j.kind != 3) {
@@ -197,6 +199,16 @@ void run_job(Ctx& cx, const Job& j) {
       const bool want_grad = j.kind >= 0 && j.kind <= 2;
       if (want_grad && cx.reuse_visibility) vis = cx.buf("vis").as<uint32_t>((size_t)j.L * P.spp * P.words_per_row);
       P.chunk = forward_chunk(cx);                                                       // sample slots per warp pass
+      const double* d_jw = nullptr; const double* d_jg = nullptr;
+      if (j.jlen > 0) {
+        // jitter/TG.cpp:271-356: raw coarse histogram, then T = hist (*) jitter_weight shifted by weight_offset
+        d_jw = stage_in(cx, "in_jw", j.jw, (size_t)j.jlen, st);
+        d_jg = stage_in(cx, "in_jg", j.jg, (size_t)j.jlen, st);
+        double* hist = cx.buf("jit_hist").as<double>(LB);
+        NLOS_CUDA_OK(cudaMemsetAsync(hist, 0, LB * sizeof(double), st));
+        launch_forward(cx, sc, P, j.ggx, hist, vis, d_wprefix);
+        launch_jitter_conv(cx, hist, d_jw, j.jlen, j.joff, j.numBins, j.L, o_T.dev);
+      } else
       launch_forward(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
       if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st));
       if (want_grad) {
@@ -209,6 +221,12 @@ void run_job(Ctx& cx, const Job& j) {
         // ---- K4/K5: gradient
         P.chunk = auto_chunk(cx, "chunk_gradient", j.F, j.L, cx.chunk_gradient > 0 ? cx.chunk_gradient : 256);
         const int64_t Lnorm = cx.num_sources_global > 0 ? cx.num_sources_global : j.L;
+        if (j.jlen > 0) {
+          double* jA = cx.buf("jit_A").as<double>((size_t)j.L * (j.numBins + 1));
+          double* jB = cx.buf("jit_B").as<double>((size_t)j.L * (j.numBins + 1));
+          launch_jitter_tables(cx, diff, d_jw, d_jg, j.jlen, j.joff, j.numBins, j.L, jA, jB);
+          P.jitter = 1; P.jA = jA; P.jB = jB;
+        }
         if (j.kind == 0) {
           double* acc = cx.buf("grad_acc").as<double>(3 * (size_t)j.V);
           NLOS_CUDA_OK(cudaMemsetAsync(acc, 0, 3 * (size_t)j.V * sizeof(double), st));
@@ -481,6 +499,28 @@ int nlos_streamed_render_normal_smoothing(nlos_ctx* ctx, const float* verticesD,
 
 int nlos_streamed_render_curvature_grad(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD, int numTriangles, double* curvature_grad) {
   return run_regulariser(ctx, 1, verticesD, numVertices, trianglesD, numTriangles, nullptr, curvature_grad, nullptr);
+}
+
+int nlos_jitter_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD, const float* verticesD, int numVertices,
+                                          const float* vertexNormal, const float* vertexAlbedo, const int* trianglesD, int numTriangles, int numSamples,
+                                          float lb, float ub, float res, const double* weight, int weight_offset, int weight_length, double* transient,
+                                          double* pathlengths, int numBins) {
+  if (!weight || weight_length <= 0) return NLOS_ERR_INVALID;
+  Job j = base_job(originD, numSources, normalD, verticesD, numVertices, vertexNormal, vertexAlbedo, trianglesD, numTriangles, numSamples, lb, ub, res, numBins, 1, 1);
+  j.transient = transient; j.pathlengths = pathlengths; j.kind = -1; j.jw = weight; j.jg = weight; j.joff = weight_offset; j.jlen = weight_length;
+  return guarded(ctx, j);
+}
+
+int nlos_jitter_streamed_render_gradient(nlos_ctx* ctx, const double* data, const double* weight, const float* originD, int measurement, const float* normalD,
+                                         const float* verticesD, int numVertices, const float* vertexNormal, const int* trianglesD, int numTriangles,
+                                         int numSamples, float lb, float ub, float res, const double* jitter_weight, const double* jitter_grad,
+                                         int weight_offset, int weight_length, double* transient, double* pathlengths, double* gradient, int testing_flag,
+                                         int numBins) {
+  if (!jitter_weight || !jitter_grad || weight_length <= 0) return NLOS_ERR_INVALID;
+  Job j = base_job(originD, measurement, normalD, verticesD, numVertices, vertexNormal, nullptr, trianglesD, numTriangles, numSamples, lb, ub, res, numBins, 1, 1);
+  j.data = data; j.weight = weight; j.transient = transient; j.pathlengths = pathlengths; j.gradient = gradient; j.testing_flag = testing_flag;
+  j.kind = 0; j.jw = jitter_weight; j.jg = jitter_grad; j.joff = weight_offset; j.jlen = weight_length;
+  return guarded(ctx, j);
 }
 
 static int run_ray_query(nlos_ctx* ctx, int mode, const float* originsD, const float* directionsD, int num_ray, const float* verticesD, int num_vertices,

@@ -46,6 +46,11 @@ struct RenderParams {
   int testing_flag;
   int chunk;                // sources per blockIdx.y
   int words_per_row;        // vis words per (source, k): ceil(F/32)
+  // temporal kernel of the gradient: Gaussian taps (smoothed_transient/, ggx/) or the tabulated SPAD jitter kernel (jitter/)
+  int jitter;               // 1: A/B sums come from the per-source tables jA/jB [L, numBins+1] indexed by the coarse bin
+  const double* jA;         // sum_i jitter_weight[i] * (-2) diff[s, b+i-offset]
+  const double* jB;         // sum_i jitter_grad[i]   * (-2) diff[s, b+i-offset]
+  double grad_coef;         // factor of the kernel-derivative term: 2/sigma^2 (Gaussian) or -2/res (jitter/TG.cpp:950)
 };
 
 struct Status { int code = 0; std::string msg; };

@@ -278,20 +278,27 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
       if (!USE_VIS) { const Ray ray = make_ray(o, d); if (occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim)) continue; }
       const float alb = shading_albedo<HAS_VA>(t, g);
       const float ff = c2 * c3 / hl / hl;
-      // K-tap sums against the residual row, grouped per coarse bin (DESIGN.md "K-tap restructuring")
-      const double x = ((double)(2.0f * hl) - (double)P.lb) * P.inv_res_fine;
-      const int64_t m0 = (int64_t)floor(x);
-      int64_t b0 = floordiv(m0 - half, P.r_grad), b1 = floordiv(m0 + half, P.r_grad);
-      if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
       double At = 0.0, Bt = 0.0;
-      const double* drow = diff + s * P.numBins;
-      for (int64_t b = b0; b <= b1; ++b) {
-        int ilo, ihi; tap_span(m0, (int)b, P.r_grad, half, P.K, ilo, ihi);
-        const double df = __ldg(drow + b);
-        At += (s_w[ihi] - s_w[ilo]) * df;
-        Bt += (s_d[ihi] - s_d[ilo]) * df;
+      if (P.jitter) {
+        // jitter/TG.cpp:947-972: taps sit on WHOLE-bin offsets, so both sums depend only on (source, coarse bin) -> tables
+        const int64_t b0 = (int64_t)floorf((2.0f * hl - P.lb) / P.res);
+        if (b0 < 0 || b0 > P.numBins) continue;
+        At = __ldg(P.jA + s * (P.numBins + 1) + b0); Bt = __ldg(P.jB + s * (P.numBins + 1) + b0);
+      } else {
+        // K-tap sums against the residual row, grouped per coarse bin (DESIGN.md "K-tap restructuring")
+        const double x = ((double)(2.0f * hl) - (double)P.lb) * P.inv_res_fine;
+        const int64_t m0 = (int64_t)floor(x);
+        int64_t b0 = floordiv(m0 - half, P.r_grad), b1 = floordiv(m0 + half, P.r_grad);
+        if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+        const double* drow = diff + s * P.numBins;
+        for (int64_t b = b0; b <= b1; ++b) {
+          int ilo, ihi; tap_span(m0, (int)b, P.r_grad, half, P.K, ilo, ihi);
+          const double df = __ldg(drow + b);
+          At += (s_w[ihi] - s_w[ilo]) * df;
+          Bt += (s_d[ihi] - s_d[ilo]) * df;
+        }
+        At *= -2.0; Bt *= -2.0;
       }
-      At *= -2.0; Bt *= -2.0;
       if (KIND == 1) {                                                // TG.cpp:677-688
         const double g0 = (double)(ff * ff);
         gs += (double)t.st.A * (g0 * At) / (double)P.spp;
@@ -327,9 +334,9 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
         }
         f3 t2 = n * inten;                                            // :956
         t2 = (t2 + gn) / (2 * t.st.A);                                // :966
-        // sum_i g_k(i) = (t1 b_k + t2 x e_k) At + (2 I / sigma^2) d b_k Bt
+        // sum_i g_k(i) = (t1 b_k + t2 x e_k) At + grad_coef I d b_k Bt   (grad_coef = 2/sigma^2, or -2/res for the jitter kernel)
         const float fa = (float)At;
-        const float fb = (float)((double)inten * P.two_over_sigma2 * Bt);
+        const float fb = (float)((double)inten * P.grad_coef * Bt);
         const float sA = t.st.A;
         const double inv_spp = 1.0 / (double)P.spp;
         f3 gk;
@@ -387,6 +394,27 @@ __global__ void __launch_bounds__(kBlock) k_visibility(const DeviceScene sc, con
     }
   }
   if (counters) { atomicAdd(counters, nr); atomicAdd(counters + 1, nb); atomicAdd(counters + 2, nt); }
+}
+
+// ---- jitter/ temporal kernel
+// forward (jitter/TG.cpp:331-350): T[s,b] = sum_i w[i] * H[s, b + offset - i]
+__global__ void k_jitter_conv(const double* __restrict__ H, const double* __restrict__ w, int J, int off, int B, size_t n, double* __restrict__ T) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = i / B; const int b = (int)(i - s * B);
+    double acc = 0.0;
+    for (int k = 0; k < J; ++k) { const int m = b + off - k; if (m >= 0 && m < B) acc += w[k] * H[s * B + m]; }
+    T[i] = acc;
+  }
+}
+// gradient tables: jA[s,b] = sum_i w[i] (-2) diff[s, b+i-off], jB likewise with the kernel derivative; b in [0,B]
+__global__ void k_jitter_tables(const double* __restrict__ diff, const double* __restrict__ w, const double* __restrict__ g, int J, int off, int B, size_t n,
+                                double* __restrict__ jA, double* __restrict__ jB) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = i / (B + 1); const int b = (int)(i - s * (B + 1));
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < J; ++k) { const int m = b + k - off; if (m >= 0 && m < B) { const double d = -2.0 * diff[s * B + m]; a += w[k] * d; c += g[k] * d; } }
+    jA[i] = a; jB[i] = c;
+  }
 }
 
 __global__ void k_pack4(const float* __restrict__ in, float4* __restrict__ out, size_t n) {
@@ -497,6 +525,17 @@ void launch_visibility(Ctx& cx, const DeviceScene& sc, const RenderParams& P, ui
   k_visibility<<<sample_grid(sc, P), kBlock, 0, cx.stream>>>(sc, P, vis_out, counters);
   cx.launches += 1;
   NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_jitter_conv(Ctx& cx, const double* H, const double* w, int J, int off, int B, int64_t L, double* T) {
+  const size_t n = (size_t)L * B; if (n == 0) return;
+  k_jitter_conv<<<(int)std::min<size_t>((n + 255) / 256, 148 * 32), 256, 0, cx.stream>>>(H, w, J, off, B, n, T);
+  cx.launches += 1; NLOS_CUDA_OK(cudaGetLastError());
+}
+void launch_jitter_tables(Ctx& cx, const double* diff, const double* w, const double* g, int J, int off, int B, int64_t L, double* jA, double* jB) {
+  const size_t n = (size_t)L * (B + 1); if (n == 0) return;
+  k_jitter_tables<<<(int)std::min<size_t>((n + 255) / 256, 148 * 32), 256, 0, cx.stream>>>(diff, w, g, J, off, B, n, jA, jB);
+  cx.launches += 1; NLOS_CUDA_OK(cudaGetLastError());
 }
 
 void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n) {

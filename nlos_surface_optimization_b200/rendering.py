@@ -88,7 +88,9 @@ def inverseRendering(mesh, data, weight, opt):
         ggx.renderStreamedGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, mesh.alpha, opt.sample_num, lo, hi, res, transient, pathlengths,
                                    gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag)
     elif getattr(opt, 'jitter', False):
-        raise NotImplementedError('the SPAD-jitter temporal kernel (jitter/) is out of scope for this build (SURVEY.md 8f row N3)')
+        from . import jitter
+        jitter.renderStreamedGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, res, opt.jitter_weight,
+                                      opt.jitter_grad, opt.jitter_offset, transient, pathlengths, gradient, data, weight, opt.testing_flag)
     elif getattr(opt, 'albedo_flag', False):
         albedo = (np.ones(mesh.v.shape[0], dtype=np.float32, order='C') * mesh.albedo).astype(np.float32)
         renderer.renderStreamedGradientWithAlbedo(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, albedo, opt.sample_num, lo, hi, res, transient,

@@ -720,3 +720,98 @@ int nlos_oracle_threads(void) {
 }
 
 }  // extern "C"
+
+// ==================================================================================== jitter/ (SPAD jitter kernel), SURVEY 8f N3
+// forward: jitter/transient_and_gradient.cpp:271-356 — coarse histogram, full convolution with the tabulated kernel,
+// T[s,b] = y[b + weight_offset];   gradient: :485-545 driver, :818-979 task (per-tap loop over whole-bin offsets)
+namespace {
+static void jitter_forward(const Scene& sc, const Params& p, const double* jw, int joff, int jlen, double* transient) {
+  std::vector<double> hist((size_t)p.L * p.numBins, 0.0);
+  render_transients(sc, p, 1, 1, hist.data(), nullptr, nullptr);
+  const int B = p.numBins;
+  std::memset(transient, 0, sizeof(double) * p.L * B);
+#pragma omp parallel for schedule(static)
+  for (int64_t src = 0; src < p.L; ++src) {
+    std::vector<double> y((size_t)B + jlen - 1, 0.0);
+    const double* x = hist.data() + src * B;
+    for (int m = 0; m < B; ++m) { double xv = x[m]; if (xv == 0.0) continue; for (int i = 0; i < jlen; ++i) y[m + i] += jw[i] * xv; }
+    for (int b = 0; b < B; ++b) { int idx = b + joff; if (idx >= 0 && idx < B + jlen - 1) transient[src * B + b] += y[idx]; }
+  }
+}
+static void jitter_gradients(const Scene& sc, const Params& p, const double* jw, const double* jg, int joff, int jlen, const double* diff, double* gradient, int testing_flag) {
+  const int spp = spp_of(p); const int B = p.numBins; const size_t G = (size_t)3 * p.V;
+  int nth = 1;
+#ifdef _OPENMP
+  nth = omp_get_max_threads();
+#endif
+  std::vector<double> accs((size_t)nth * G, 0.0);
+#pragma omp parallel
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    double* g_acc = accs.data() + (size_t)tid * G;
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t src = 0; src < p.L; ++src) {
+      V3 o_n = ld3(p.onormal, src);
+      for (int f = 0; f < p.F; ++f) {
+        TriSetup ts = setup_tri(p, f);
+        for (int k = 0; k < spp; ++k) {
+          Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+          if (!sm.visible || !sm.in_range) continue;
+          V3 n = shading_normal(p, ts, sm); float alb = shading_albedo(p, ts, sm);
+          V3 d = sm.d; float hl = sm.r;
+          float c2 = dot3(o_n, d), c3 = dot3(n, -d); if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+          float ff = c2 * c3 / hl / hl; double intensity = alb * ff * ff;
+          V3 t1 = (2 * alb * c2 * c3) * (o_n * c3 - n * c2 + (4 * (-d)) * c2 * c3); t1 = t1 / powf(hl, 5);
+          V3 gn = mk(0, 0, 0);
+          if (testing_flag == 0 && p.vnormal) { gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / powf(hl, 4); float ct = dot3(gn, n); gn = gn - n * ct; }
+          V3 t2 = n * (float)intensity; t2 = (t2 + gn) / (2 * ts.A);
+          const V3 x1 = cross3(t2, ts.v3 - ts.v2), x2 = cross3(t2, ts.v1 - ts.v3), x3 = cross3(t2, ts.v2 - ts.v1);
+          const int64_t b0 = (int64_t)floorf((2.0f * hl - p.lb) / p.res);
+          for (int i = 0; i < jlen; ++i) {                                   // jitter/TG.cpp:947-972
+            const int64_t bin = b0 + (i - joff);
+            if (bin < 0 || bin >= B) continue;
+            const float wk = (float)jw[i];
+            const V3 jt = (float)(jg[i] * intensity * (-2)) * d / p.res;
+            const float df = (float)((-2) * diff[src * B + bin]);
+            V3 g;
+            g = (t1 * wk + jt) * sm.u + x1 * wk; g = g * df;
+            g_acc[3 * ts.i1] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i1 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i1 + 2] += (double)(ts.A * g.z) / (double)spp;
+            g = (t1 * wk + jt) * sm.v + x2 * wk; g = g * df;
+            g_acc[3 * ts.i2] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i2 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i2 + 2] += (double)(ts.A * g.z) / (double)spp;
+            g = (t1 * wk + jt) * sm.w + x3 * wk; g = g * df;
+            g_acc[3 * ts.i3] += (double)(ts.A * g.x) / (double)spp; g_acc[3 * ts.i3 + 1] += (double)(ts.A * g.y) / (double)spp; g_acc[3 * ts.i3 + 2] += (double)(ts.A * g.z) / (double)spp;
+          }
+        }
+      }
+    }
+  }
+  for (int t = 0; t < nth; ++t) for (size_t d = 0; d < G; ++d) gradient[d] += accs[(size_t)t * G + d] / (double)p.L;
+}
+}  // namespace
+
+extern "C" {
+int nlos_oracle_jitter_transient(const float* origin, int64_t L, const float* onormal, const float* verts, int V, const float* vnormal, const float* valbedo,
+                                 const int32_t* faces, int F, int num_samples, float lb, float ub, float res, int numBins, const double* jw, int joff, int jlen,
+                                 double* transient, double* pathlengths, uint64_t seed, int64_t src_offset, int mode) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, valbedo, faces, F, -1.f, num_samples, lb, ub, res, numBins, seed, src_offset);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  jitter_forward(sc, p, jw, joff, jlen, transient);
+  return 0;
+}
+int nlos_oracle_jitter_gradient(const double* data, const double* weight, const float* origin, int64_t L, const float* onormal, const float* verts, int V,
+                                const float* vnormal, const int32_t* faces, int F, int num_samples, float lb, float ub, float res, int numBins,
+                                const double* jw, const double* jg, int joff, int jlen, double* transient, double* pathlengths, double* gradient,
+                                int testing_flag, uint64_t seed, int64_t src_offset, int mode) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, nullptr, faces, F, -1.f, num_samples, lb, ub, res, numBins, seed, src_offset);
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  jitter_forward(sc, p, jw, joff, jlen, transient);                        // jitter/SSG.cpp:525-543
+  std::vector<double> diff; make_difference(p, data, weight, transient, 0, diff);   // :544-547 (no loss_test)
+  jitter_gradients(sc, p, jw, jg, joff, jlen, diff.data(), gradient, testing_flag);
+  return 0;
+}
+}

@@ -194,3 +194,33 @@ def bary_to_world(vertices, faces, bary):
     out = np.zeros((bary.shape[0], 3), dtype=np.float32)
     lib().nlos_oracle_bary_to_world(_p(vertices, C.c_float), _p(faces, C.c_int32), _p(bary, C.c_float), C.c_int64(bary.shape[0]), _p(out, C.c_float))
     return out
+
+
+def jitter_transient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, jitter_weight, jitter_offset, vertex_normal=None,
+                     vertex_albedo=None, seed=DEFAULT_SEED, src_offset=0, brute=False):
+    origin = _f32(origin); normal = _f32(normal); vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vn = None if vertex_normal is None else _f32(vertex_normal); va = None if vertex_albedo is None else _f32(vertex_albedo)
+    jw = np.ascontiguousarray(jitter_weight, dtype=np.float64).reshape(-1)
+    L, V, F = origin.shape[0], vertices.shape[0], faces.shape[0]; B = num_bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B)
+    lib().nlos_oracle_jitter_transient(_p(origin, C.c_float), C.c_int64(L), _p(normal, C.c_float), _p(vertices, C.c_float), C.c_int(V), _p(vn, C.c_float),
+                                       _p(va, C.c_float), _p(faces, C.c_int32), C.c_int(F), C.c_int(num_sample), C.c_float(lower), C.c_float(upper),
+                                       C.c_float(resolution), C.c_int(B), _p(jw, C.c_double), C.c_int(jitter_offset), C.c_int(jw.shape[0]),
+                                       _p(T, C.c_double), _p(pl, C.c_double), C.c_uint64(seed), C.c_int64(src_offset), C.c_int(1 if brute else 0))
+    return T, pl
+
+
+def jitter_gradient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, jitter_weight, jitter_grad, jitter_offset, data, weight,
+                    testing_flag=1, vertex_normal=None, seed=DEFAULT_SEED, src_offset=0, brute=False):
+    origin = _f32(origin); normal = _f32(normal); vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vn = None if vertex_normal is None else _f32(vertex_normal)
+    jw = np.ascontiguousarray(jitter_weight, dtype=np.float64).reshape(-1); jg = np.ascontiguousarray(jitter_grad, dtype=np.float64).reshape(-1)
+    data = np.ascontiguousarray(data, dtype=np.float64); weight = np.ascontiguousarray(weight, dtype=np.float64)
+    L, V, F = origin.shape[0], vertices.shape[0], faces.shape[0]; B = num_bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((V, 3))
+    lib().nlos_oracle_jitter_gradient(_p(data, C.c_double), _p(weight, C.c_double), _p(origin, C.c_float), C.c_int64(L), _p(normal, C.c_float),
+                                      _p(vertices, C.c_float), C.c_int(V), _p(vn, C.c_float), _p(faces, C.c_int32), C.c_int(F), C.c_int(num_sample),
+                                      C.c_float(lower), C.c_float(upper), C.c_float(resolution), C.c_int(B), _p(jw, C.c_double), _p(jg, C.c_double),
+                                      C.c_int(jitter_offset), C.c_int(jw.shape[0]), _p(T, C.c_double), _p(pl, C.c_double), _p(G, C.c_double),
+                                      C.c_int(testing_flag), C.c_uint64(seed), C.c_int64(src_offset), C.c_int(1 if brute else 0))
+    return T, G, pl

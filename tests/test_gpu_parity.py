@@ -354,3 +354,27 @@ def test_embree_intersector_api(oracle, gpu_ctx):
         # the hit point lies on the ray
         t = np.linalg.norm(p[hit] - o[hit], axis=1) / np.linalg.norm(d[hit], axis=1)
         assert np.abs(o[hit] + t[:, None] * d[hit] - p[hit]).max() < 1e-4
+
+
+def test_jitter_temporal_kernel(oracle, gpu_ctx):
+    """tabulated SPAD-jitter kernel (asymmetric 40-tap, like jitter/jitter_info.mat) forward + vertex gradient."""
+    from nlos_surface_optimization_b200 import jitter
+    o, n, v, f, ns = _scene('ico')
+    J, off = 40, 12
+    x = np.arange(J) - off
+    jw = np.exp(-0.5 * (x / 3.0) ** 2) + 0.3 * np.exp(-np.maximum(x, 0) / 8.0) * (x > 0); jw /= jw.sum()
+    jg = np.gradient(jw)
+    jw2 = np.ascontiguousarray(jw.reshape(J, 1)); jg2 = np.ascontiguousarray(jg.reshape(J, 1))
+    T_ref, pl_ref = oracle.jitter_transient(o, n, v, f, ns, LB, UB, RES, jw, off)
+    B = T_ref.shape[1]
+    T = np.full((o.shape[0], B), 3.0); pl = np.zeros(B)
+    jitter.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, T, pl, jw2, off, ctx=gpu_ctx)
+    assert np.array_equal(pl, pl_ref) and rel_l2(T, T_ref) <= TOL_TRANSIENT
+    v2 = v.copy(); v2[:, 2] += 0.01
+    data = oracle.jitter_transient(o, n, v2, f, ns, LB, UB, RES, jw, off)[0]; weight = np.ones_like(data)
+    for tf in (1,):
+        T_ref, G_ref, _ = oracle.jitter_gradient(o, n, v, f, ns, LB, UB, RES, jw, jg, off, data, weight, testing_flag=tf)
+        T = np.zeros((o.shape[0], B)); G = np.zeros((v.shape[0], 3))
+        jitter.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, jw2, jg2, off, T, pl, G, data, weight, tf, ctx=gpu_ctx)
+        assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+        assert np.linalg.norm(G_ref) > 0 and rel_l2(G, G_ref) <= TOL_GRADIENT

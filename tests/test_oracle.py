@@ -350,3 +350,31 @@ def test_ray_query_oracle_bvh_equals_brute_force(oracle):
     p = oracle.bary_to_world(v, f, b3)
     t = np.linalg.norm(p[hit] - o[hit], axis=1) / np.linalg.norm(d[hit], axis=1)
     assert np.abs(o[hit] + t[:, None] * d[hit] - p[hit]).max() < 1e-5
+
+
+def test_jitter_kernel_restatement(oracle):
+    """jitter/: a delta kernel reproduces the raw histogram, a shifted delta shifts it, energy is conserved, and the vertex
+    gradient with (jitter_weight, jitter_grad) = a sampled Gaussian matches the Gaussian-tap gradient of smoothed_transient/."""
+    from nlos_surface_optimization_b200 import scenes
+    v, f = scenes.icosphere(2, 0.1, (0, 0, 0.45)); o, n = scenes.wall_grid(2); ns = 4000
+    H = oracle.transient(o, n, v, f, ns, LB, UB, RES)[0]
+    delta = np.zeros(9); delta[4] = 1.0
+    assert np.array_equal(oracle.jitter_transient(o, n, v, f, ns, LB, UB, RES, delta, 4)[0], H)
+    Ts = oracle.jitter_transient(o, n, v, f, ns, LB, UB, RES, delta, 1)[0]          # offset 1: T[b] = H[b + 1 - 4]
+    assert np.array_equal(Ts[:, 3:], H[:, :-3])
+    J, off = 41, 20
+    x = np.arange(J) - off
+    w = np.exp(-0.5 * (x / 2.0) ** 2); w /= w.sum()
+    T = oracle.jitter_transient(o, n, v, f, ns, LB, UB, RES, w, off)[0]
+    assert abs(T.sum() - H.sum()) < 1e-9 * H.sum()
+    # whole-bin Gaussian taps: jitter gradient == Gaussian gradient built from the same taps (refine_scale=1 => taps on whole bins)
+    s_bin = 10
+    wg, sigma2 = oracle.taps(RES, 1, s_bin)                                           # K = 4*1*10+1 = 41 taps, delta_i = (i-20)*res
+    delta_i = (np.arange(41) - 20) * np.float32(RES)
+    jg = wg * delta_i / sigma2 * 2 * (-np.float32(RES) / 2.0)                         # so that jg*(-2)/res == w*delta/sigma^2*2
+    D = np.random.RandomState(0).rand(*H.shape)
+    # same residual for both: data = T_forward + D with each path's own forward
+    Tj = oracle.jitter_transient(o, n, v, f, ns, LB, UB, RES, wg, 20)[0]
+    _, Gj, _ = oracle.jitter_gradient(o, n, v, f, ns, LB, UB, RES, wg, jg, 20, Tj + D, np.ones_like(D))
+    _, Gg, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, H + D, np.ones_like(D), 1, s_bin)       # sigma>=5 & r=1: forward raw
+    assert rel_l2(Gj, Gg) < 1e-5
