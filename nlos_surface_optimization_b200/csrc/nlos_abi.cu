@@ -20,6 +20,8 @@ Ctx::~Ctx() {
   for (auto& kv : bufs) kv.second.release();
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   if (ev_copy) cudaEventDestroy(ev_copy);
+  if (ev_fwd) cudaEventDestroy(ev_fwd);
+  if (ev_start) cudaEventDestroy(ev_start);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -61,9 +63,9 @@ OutView<T> stage_out(Ctx& cx, const char* name, T* p, size_t n, bool upload_curr
   return v;
 }
 template <class T>
-bool finish_out(Ctx& cx, const OutView<T>& v) {
+bool finish_out(Ctx& cx, const OutView<T>& v, cudaStream_t on = nullptr) {
   if (!v.host) return false;
-  NLOS_CUDA_OK(cudaMemcpyAsync(v.host, v.dev, v.n * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+  NLOS_CUDA_OK(cudaMemcpyAsync(v.host, v.dev, v.n * sizeof(T), cudaMemcpyDeviceToHost, on ? on : cx.stream));
   return true;
 }
 
@@ -110,7 +112,7 @@ int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
 }
 
 // forward kernel: sample slots (source*spp + k) per warp pass, bounded by the visibility tile in shared memory
-int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 256; return std::min(std::max(c, 1), 256); }
+int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 64; return std::min(std::max(c, 1), 256); }
 
 void run_job(Ctx& cx, const Job& j) {
   NLOS_CUDA_OK(cudaSetDevice(cx.device));
@@ -130,6 +132,9 @@ void run_job(Ctx& cx, const Job& j) {
   cudaStream_t st = cx.stream;
   const bool timing = cx.timing_enabled != 0;
   if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[0], st));
+  // the copy stream may only touch the staging buffers after every EARLIER call on the main stream has finished with them
+  NLOS_CUDA_OK(cudaEventRecord(cx.ev_start, st));
+  NLOS_CUDA_OK(cudaStreamWaitEvent(cx.copy_stream, cx.ev_start, 0));
   const size_t LB = (size_t)j.L * (size_t)std::max(j.numBins, 0);
 
   // ---- stage inputs
@@ -151,7 +156,7 @@ void run_job(Ctx& cx, const Job& j) {
   if (j.kind == 0) o_G = stage_out(cx, "out_gradient", j.gradient, 3 * (size_t)j.V, true);
   if (j.kind == 3) o_I = stage_out(cx, "out_intensity", j.intensity, (size_t)j.F, true);
 
-  bool need_sync = false;
+  bool need_sync = false, fwd_recorded = false;
   if (j.F > 0 && j.L > 0) {
     // ---- K0: scene
     DeviceScene sc;
@@ -211,15 +216,19 @@ void run_job(Ctx& cx, const Job& j) {
       } else
       launch_forward(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
       if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st));
+      NLOS_CUDA_OK(cudaEventRecord(cx.ev_fwd, st)); fwd_recorded = true;        // the transient is final here
       if (want_grad) {
         // ---- K3: residual
-        const double* d_data = stage_in(cx, "in_data", j.data, LB, st);
-        const double* d_weight = stage_in(cx, "in_weight", j.weight, LB, st);
+        // host data/weight ride the copy stream while the forward kernel (already enqueued) runs
+        const double* d_data = stage_in(cx, "in_data", j.data, LB, cx.copy_stream);
+        const double* d_weight = stage_in(cx, "in_weight", j.weight, LB, cx.copy_stream);
+        NLOS_CUDA_OK(cudaEventRecord(cx.ev_copy, cx.copy_stream));
+        NLOS_CUDA_OK(cudaStreamWaitEvent(st, cx.ev_copy, 0));
         double* diff = cx.buf("diff").as<double>(LB);
         launch_residual(cx, d_data, d_weight, o_T.dev, diff, LB, j.loss_flag);
         if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st));
         // ---- K4/K5: gradient
-        P.chunk = auto_chunk(cx, "chunk_gradient", j.F, j.L, cx.chunk_gradient > 0 ? cx.chunk_gradient : 256);
+        P.chunk = auto_chunk(cx, "chunk_gradient", j.F, j.L, cx.chunk_gradient > 0 ? cx.chunk_gradient : 128);
         const int64_t Lnorm = cx.num_sources_global > 0 ? cx.num_sources_global : j.L;
         if (j.jlen > 0) {
           double* jA = cx.buf("jit_A").as<double>((size_t)j.L * (j.numBins + 1));
@@ -250,12 +259,18 @@ void run_job(Ctx& cx, const Job& j) {
   }
 
   // ---- results back to host arrays
-  need_sync |= finish_out(cx, o_T);
+  bool copy_sync = false;
+  if (o_T.host && fwd_recorded && j.kind >= 0 && j.kind <= 2) {
+    // the transient's D2H overlaps the gradient kernels (all already enqueued on the main stream)
+    NLOS_CUDA_OK(cudaStreamWaitEvent(cx.copy_stream, cx.ev_fwd, 0));
+    copy_sync = finish_out(cx, o_T, cx.copy_stream);
+  } else need_sync |= finish_out(cx, o_T);
   need_sync |= finish_out(cx, o_pl);
   need_sync |= finish_out(cx, o_G);
   need_sync |= finish_out(cx, o_I);
   if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[5], st));
   if (need_sync || timing) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+  if (copy_sync) NLOS_CUDA_OK(cudaStreamSynchronize(cx.copy_stream));
   if (timing) {
     cudaEventElapsedTime(&cx.timing.build_ms, cx.ev[0], cx.ev[1]);
     cudaEventElapsedTime(&cx.timing.forward_ms, cx.ev[1], cx.ev[2]);
@@ -309,6 +324,8 @@ int nlos_ctx_create(int device, nlos_ctx** out) {
     NLOS_CUDA_OK(cudaStreamCreateWithFlags(&c->cx.copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c->cx.ev) NLOS_CUDA_OK(cudaEventCreate(&ev));
     NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_copy, cudaEventDisableTiming));
+    NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_fwd, cudaEventDisableTiming));
+    NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_start, cudaEventDisableTiming));
   } catch (const std::exception& ex) { g_create_error = ex.what(); delete c; return NLOS_ERR_CUDA; }
   *out = c;
   return NLOS_OK;

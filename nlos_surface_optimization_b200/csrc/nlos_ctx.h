@@ -34,7 +34,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
-  cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_copy = nullptr;   // data/weight staged on copy_stream
+  cudaEvent_t ev_start = nullptr;  // start of the current call on the main stream
+  cudaEvent_t ev_fwd = nullptr;    // forward transient final (its D2H may start while the gradient runs)
   std::string last_error;
   // options (nlos_ctx_set_*)
   uint64_t seed = 5489;          // boost::mt19937 default = the reference's built-in seed (sampler.cpp:25)

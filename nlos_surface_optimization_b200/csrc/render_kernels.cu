@@ -78,6 +78,8 @@ struct WarpShared {
   int meta[kQCap];               // slot_local | tri_lane << 16
   unsigned tile[kTile];          // one visibility word (32 triangles) per slot
 };
+// (Per-lane stacks stay in local memory: moving them to shared memory [level][lane] was measured 33 % SLOWER — the 32 KB
+//  per block it costs shrink the L1 that keeps the 13.5 MB of nodes + triangles hot.)
 
 // MODE 0: transient histogram (+ optional visibility bits);  MODE 1: per-triangle intensity (K6)
 template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
@@ -435,6 +437,10 @@ void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, dou
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
   const dim3 grid((unsigned)((sc.F + kBlock - 1) / kBlock), (unsigned)std::min<int64_t>(nchunks, 65535), 1);
   const size_t smem = (kBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
+  if (smem > 48 * 1024) {      // long tap tables (large refine_scale * sigma_bin) need the opt-in shared-memory limit
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward<GGX, VN, VA, SMOOTH, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   cx.launches += 1;
