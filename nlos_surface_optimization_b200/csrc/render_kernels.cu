@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const De
     int gen = 0, qhead = 0, qcount = 0;
     // per-lane traversal state of the ray in flight (cur == kSentinel: lane is idle)
     int cur = kSentinel, sp = 0, stack[kStack];
+#if defined(NLOS_EXPERIMENT_EXTRALOAD) || defined(NLOS_EXPERIMENT_EXTRAALU)
+    float sink = 0.f;
+#endif
     Ray ray; float ts = 0.f, val = 0.f; int bin = -1, prim = 0, tri_lane = 0, slot_local = 0; int64_t src = 0;
     ray.o = ray.d = ray.id = ray.oid = mk3(0.f, 0.f, 0.f);
     for (;;) {
@@ -179,6 +182,15 @@ __global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const De
         float4 a, b, c, dq;
         ld256(&sc.nodes[cur].a, a, b);
         ld256(&sc.nodes[cur].c, c, dq);
+#ifdef NLOS_EXPERIMENT_EXTRALOAD     // timing experiment only: one redundant 32-byte node fetch per step (same line) to probe L1-boundness
+        { float e0, e1, e2, e3, e4, e5, e6, e7;
+          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(e0), "=f"(e1), "=f"(e2), "=f"(e3), "=f"(e4), "=f"(e5), "=f"(e6), "=f"(e7) : "l"(&sc.nodes[cur].a)); sink += e0 + e4; }
+#endif
+#ifdef NLOS_EXPERIMENT_EXTRAALU      // timing experiment only: 12 redundant min/max per step to probe ALU/issue-boundness
+        { float z = a.x;
+#pragma unroll
+          for (int q = 0; q < 12; ++q) asm volatile("min.f32 %0, %0, %1;" : "+f"(z) : "f"(b.x + (float)q)); sink += z; }
+#endif
         const int r0 = __float_as_int(dq.x), r1 = __float_as_int(dq.y);
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
@@ -218,6 +230,9 @@ __global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const De
         cur = kSentinel;
       }
     }
+#if defined(NLOS_EXPERIMENT_EXTRALOAD) || defined(NLOS_EXPERIMENT_EXTRAALU)
+    if (sink == 1234.5678f) out[0] = sink;
+#endif
     if (WRITE_VIS) {
       __syncwarp();
       if (warp_global * 32 < sc.F) for (int i = lane; i < nslots; i += 32) vis[(size_t)(slot0 + i) * P.words_per_row + warp_global] = ws.tile[i];

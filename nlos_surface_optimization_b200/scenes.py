@@ -42,9 +42,23 @@ def merge(meshes):
     return np.ascontiguousarray(np.concatenate(vs), dtype=np.float32), np.ascontiguousarray(np.concatenate(fs), dtype=np.int32)
 
 
-def bunny():
-    d = np.load(os.path.join(_ASSETS, 'bunny.npz'))
+def _asset(name):
+    d = np.load(os.path.join(_ASSETS, name + '.npz'))
     return np.ascontiguousarray(d['v'], dtype=np.float32), np.ascontiguousarray(d['f'], dtype=np.int32)
+
+
+def bunny():
+    return _asset('bunny')
+
+
+def armadillo():
+    """GT armadillo (exp_armadillo/setup/armadillo.obj, V=43 243 F=86 482)."""
+    return _asset('armadillo')
+
+
+def armadillo_init():
+    """CNLOS-thresholded initial mesh the optimisation loop starts from (exp_armadillo/setup/cnlos_armadillo_threshold.obj)."""
+    return _asset('armadillo_init')
 
 
 def _value_noise(x, y, seed, octaves=3):

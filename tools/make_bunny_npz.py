@@ -22,10 +22,13 @@ def read_obj(path):
 
 if __name__ == '__main__':
     ref = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
-    src = os.path.join(ref, 'transient_rendering_cython', 'mesh', 'bunny_centered.obj')
-    v, f = read_obj(src)
-    # the reference loads with igl.readOBJ (double) then casts to float32 (exp_bunny/main_create_gt.py:66-67)
-    v32 = v.astype(np.float32)
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'assets', 'bunny.npz')
-    np.savez_compressed(out, v=v32, f=f)
-    print(out, v32.shape, f.shape, v32.min(0), v32.max(0), os.path.getsize(out))
+    base = os.path.join(ref, 'transient_rendering_cython')
+    for name, rel in (('bunny', 'mesh/bunny_centered.obj'),
+                      ('armadillo', 'exp_armadillo/setup/armadillo.obj'),                     # GT mesh of config C-arm
+                      ('armadillo_init', 'exp_armadillo/setup/cnlos_armadillo_threshold.obj')):  # CNLOS initialisation (exp_bunny/test.py:89-93)
+        v, f = read_obj(os.path.join(base, rel))
+        # the reference loads with igl.readOBJ (double) then casts to float32 (exp_bunny/main_create_gt.py:66-67)
+        v32 = v.astype(np.float32)
+        out = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'assets', name + '.npz')
+        np.savez_compressed(out, v=v32, f=f)
+        print(out, v32.shape, f.shape, v32.min(0), v32.max(0), os.path.getsize(out))
