@@ -378,3 +378,39 @@ def test_jitter_temporal_kernel(oracle, gpu_ctx):
         jitter.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, jw2, jg2, off, T, pl, G, data, weight, tf, ctx=gpu_ctx)
         assert rel_l2(T, T_ref) <= TOL_TRANSIENT
         assert np.linalg.norm(G_ref) > 0 and rel_l2(G, G_ref) <= TOL_GRADIENT
+
+
+def test_sharded_rendering_nccl_two_gpus(oracle, tmp_path):
+    """dist.inverse_rendering_sharded over NCCL on 2 GPUs (skipped on a 1-GPU box): all-reduced gradient and gathered
+    transient equal the single-GPU call."""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from nlos_surface_optimization_b200 import renderer, scenes
+    import nlos_surface_optimization_b200 as nb
+    o, n, v, f, ns = _scene('ico')
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    L, B = data.shape
+    T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=nb.default_context(0))
+    np.savez(str(tmp_path / 'in.npz'), o=o, n=n, v=v, f=f, data=data, weight=weight)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'w.py'
+    script.write_text('''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from nlos_surface_optimization_b200 import dist as nd
+local = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+d = np.load(%r)
+T, G, pl = nd.inverse_rendering_sharded(d['o'], d['n'], d['v'], d['f'], %d, %r, %r, %r, d['data'], d['weight'], 10, 1, device=torch.device('cuda', local), gather=True)
+if dist.get_rank() == 0: np.savez(%r, T=T, G=G)
+dist.barrier(); dist.destroy_process_group()
+''' % (root, str(tmp_path / 'in.npz'), ns, LB, UB, RES, str(tmp_path / 'out.npz')))
+    rc = subprocess.call([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29533', str(script)], timeout=600)
+    assert rc == 0
+    out = np.load(str(tmp_path / 'out.npz'))
+    assert rel_l2(out['T'], T) <= 1e-12
+    assert rel_l2(out['G'], G) <= 1e-9
