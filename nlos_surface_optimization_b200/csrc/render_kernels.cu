@@ -129,7 +129,19 @@ __global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const De
           if (active) {
             const f3 o = xyz(__ldg(P.origin + s)), on = xyz(__ldg(P.onormal + s));
             SampleGeom g;
-            if (sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
+            // Cheap exact-safe cull before any RNG: with face-normal shading, a triangle whose plane has the source clearly on
+            // its back side (and which lies clearly in front of the wall point) has n.d > 0 and n_o.d > 0 for EVERY point on
+            // it, so ff = -(n.d)(n_o.d)/r^2 < 0 and the sample adds nothing (TG.cpp:224-228).  The margins (1e-5 relative)
+            // are far above float round-off; anything closer to edge-on goes through the full path.
+            bool culled = false;
+            if (!HAS_VN) {
+              const f3 w1 = t.st.v1 - o, w2 = t.st.v2 - o, w3 = t.st.v3 - o;
+              const float m1 = 1e-5f * (fabsf(w1.x) + fabsf(w1.y) + fabsf(w1.z));
+              culled = dot3(t.st.nf, w1) > m1 && dot3(on, w1) > m1 &&
+                       dot3(on, w2) > 1e-5f * (fabsf(w2.x) + fabsf(w2.y) + fabsf(w2.z)) &&
+                       dot3(on, w3) > 1e-5f * (fabsf(w3.x) + fabsf(w3.y) + fabsf(w3.z));
+            }
+            if (!culled && sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
               const f3 n = shading_normal<HAS_VN>(t, g);
               const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
               if (ff > 0.0f) {                                                      // max(0,ff)==0 adds exactly 0 (TG.cpp:228)
