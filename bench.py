@@ -319,7 +319,9 @@ def run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s / args.steps},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'fp32', 'kernel': 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'roofline': {'bound': 'fp32', 'kernel': 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                         'traffic': 27.2e6,     # bytes: dram__bytes_read.sum + dram__bytes_write.sum of one k_forward launch, ncu --set full (profiles/r1_ncu_full_summary.txt)
+                         'traffic_unit': 'bytes of DRAM per k_forward launch (ncu); the unit of achieved/peak is TFLOP/s',
                          'peak_source': peak_how, 'flops_per_path_sample': flops_fwd_sample, 'canonical_box_tests_per_ray': box, 'canonical_tri_tests_per_ray': tri,
                          'kernel_ms': fwd_ms,
                          'note': 'achieved = CANONICAL flops (oracle nearest-hit traversal counts, SURVEY 8d) / kernel time: an effective rate; the kernel executes fewer (any-hit query, zero-contribution samples never traced)',

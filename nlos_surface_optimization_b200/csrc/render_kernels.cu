@@ -23,6 +23,10 @@ namespace nlos {
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef NLOS_FWD_BLOCK
+#define NLOS_FWD_BLOCK 128
+#endif
+constexpr int kFwdBlock = NLOS_FWD_BLOCK;   // threads per block of the forward kernel (one warp = one triangle tile)
 
 struct TriRegs {
   ShadeTri st; TriRec tr; int prim;
@@ -83,11 +87,11 @@ struct WarpShared {
 
 // MODE 0: transient histogram (+ optional visibility bits);  MODE 1: per-triangle intensity (K6)
 template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
-__global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
+__global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* ws_all = reinterpret_cast<WarpShared*>(smem_raw);
-  double* s_w = reinterpret_cast<double*>(smem_raw + (kBlock / 32) * sizeof(WarpShared));   // SMOOTH: tap prefix sums
+  double* s_w = reinterpret_cast<double*>(smem_raw + (kFwdBlock / 32) * sizeof(WarpShared));   // SMOOTH: tap prefix sums
   if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += blockDim.x) s_w[i] = wprefix[i]; __syncthreads(); }
   const int lane = threadIdx.x & 31;
   WarpShared& ws = ws_all[threadIdx.x >> 5];
@@ -207,7 +211,11 @@ __global__ void __launch_bounds__(kBlock, NLOS_FWD_MINBLOCKS) k_forward(const De
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
         const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
+#ifdef NLOS_UNORDERED     // any-hit needs no front-to-back order; measured: see DESIGN.md
+        if (h0 && h1) { stack[sp++] = r1; cur = r0; }
+#else
         if (h0 && h1) { const bool first0 = t0 <= t1; stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1; }
+#endif
         else if (h0) cur = r0;
         else if (h1) cur = r1;
         else cur = stack[--sp];
@@ -462,14 +470,14 @@ inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
-  const dim3 grid((unsigned)((sc.F + kBlock - 1) / kBlock), (unsigned)std::min<int64_t>(nchunks, 65535), 1);
-  const size_t smem = (kBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
+  const dim3 grid((unsigned)((sc.F + kFwdBlock - 1) / kFwdBlock), (unsigned)std::min<int64_t>(nchunks, 65535), 1);
+  const size_t smem = (kFwdBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
   if (smem > 48 * 1024) {      // long tap tables (large refine_scale * sigma_bin) need the opt-in shared-memory limit
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward<GGX, VN, VA, SMOOTH, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
-  else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
+  if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kFwdBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
+  else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kFwdBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   cx.launches += 1;
 }
 
