@@ -211,14 +211,23 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
         const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
-#ifdef NLOS_UNORDERED     // any-hit needs no front-to-back order; measured: see DESIGN.md
-        if (h0 && h1) { stack[sp++] = r1; cur = r0; }
+#ifndef NLOS_BRANCHY      // fully predicated child selection: no BSSY/BSYNC pair inside the step (measured 33.3 vs 35.8 ms)
+        {
+          const bool both = h0 && h1, any = h0 || h1, first0 = t0 <= t1;
+          const int nearr = (h0 && (!h1 || first0)) ? r0 : r1;
+          if (both) stack[sp] = first0 ? r1 : r0;
+          sp += both ? 1 : 0;
+          int popped = kDone;
+          if (!any) popped = stack[sp - 1];
+          sp -= any ? 0 : 1;
+          cur = any ? nearr : popped;
+        }
 #else
         if (h0 && h1) { const bool first0 = t0 <= t1; stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1; }
-#endif
         else if (h0) cur = r0;
         else if (h1) cur = r1;
         else cur = stack[--sp];
+#endif
 #if NLOS_MINLANES > 0
         if (__popc(__activemask()) < NLOS_MINLANES) break;
 #endif
