@@ -170,6 +170,32 @@ NLOS_HD bool tri_occludes(const float4* __restrict__ ttris, int j, const Ray& r,
   return t < t_self || (t == t_self && prim < prim_self);
 }
 
+// Same predicate as tri_occludes() with one combined validity test and the IEEE division only when the outcome is not already
+// decided by a 4-ulp bracket around T = t_self * |den| (the division result is what the contract compares, so the
+// undecided sliver still divides; logic only, no arithmetic of isect() is changed).
+NLOS_HD bool tri_occludes_fast(const float4* __restrict__ ttris, int j, const Ray& r, float t_self, int prim_self) {
+  float4 q0, q1, q2, q3;
+  ld256(ttris + 4 * (size_t)j, q0, q1);
+  ld256(ttris + 4 * (size_t)j + 2, q2, q3);
+  const int prim = f2i(q0.w);
+  const f3 C = xyz(q0) - r.o;
+  const f3 R = cross3(C, r.d);
+  const f3 Ng = xyz(q3);
+  const float den = dot3(Ng, r.d);
+  const float absDen = fabsf(den);
+  const float sgn = den < 0.0f ? -1.0f : 1.0f;
+  const float U = dot3(R, xyz(q2)) * sgn;
+  const float V = dot3(R, xyz(q1)) * sgn;
+  const float T = dot3(Ng, C) * sgn;
+  const bool valid = (den != 0.0f) & (U >= 0.0f) & (V >= 0.0f) & (U + V <= absDen) & (T > 0.0f) & (prim != prim_self);
+  if (!valid) return false;
+  const float ref = absDen * t_self;
+  if (T < ref * 0.99999952f) return true;          // t = T/|den| is certainly < t_self
+  if (T > ref * 1.00000048f) return false;         // certainly > t_self
+  const float t = T / absDen;
+  return t < t_self || (t == t_self && prim < prim_self);
+}
+
 // Any-hit query equivalent to "nearest hit (min t, ties -> lowest prim) is NOT prim_self".
 // num_internal = F-1 Karras nodes (root = 0); when the whole mesh is one leaf run, root_count = F.
 NLOS_HD bool occluded(const BvhNode* __restrict__ nodes, const float4* __restrict__ ttris, int root_count,

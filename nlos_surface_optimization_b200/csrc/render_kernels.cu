@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
       if (cur < 0 && cur != kDone) {
         const int first = leaf_first(cur), cnt = leaf_count(cur);
         bool occ = false;
-        for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes(sc.ttris, first + j, ray, ts, prim);
+        for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes_fast(sc.ttris, first + j, ray, ts, prim);
         cur = occ ? kSentinel : stack[--sp];                     // occluded: drop the ray
       }
       if (cur == kDone) {                                        // traversal finished without an occluder: visible

@@ -124,7 +124,7 @@ long emul_visibility(const float* origin, int L, const float* verts, int V, cons
           bit = occ ? 0 : 1;
           if (check_brute) {
             bool occ2 = false;
-            for (int j = 0; j < F && !occ2; ++j) occ2 = tri_occludes(b.ttris.data(), j, ray, g.t, prim);
+            for (int j = 0; j < F && !occ2; ++j) { occ2 = tri_occludes(b.ttris.data(), j, ray, g.t, prim); if (tri_occludes_fast(b.ttris.data(), j, ray, g.t, prim) != occ2) ++mism; }
             if (occ2 != occ) ++mism;
           }
         }
