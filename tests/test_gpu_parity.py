@@ -414,3 +414,52 @@ dist.barrier(); dist.destroy_process_group()
     out = np.load(str(tmp_path / 'out.npz'))
     assert rel_l2(out['T'], T) <= 1e-12
     assert rel_l2(out['G'], G) <= 1e-9
+
+
+def test_degenerate_sizes_and_error_paths(gpu_ctx):
+    """Empty inputs and bad arguments: no crash, zeros out, errors reported through the status code (the reference printf()s)."""
+    import ctypes as C
+    import nlos_surface_optimization_b200 as nb
+    from nlos_surface_optimization_b200 import renderer, scenes
+    v, f = scenes.quad(0.4, 0.1); B = 1200
+    # zero sources
+    o0 = np.zeros((0, 3), np.float32); T0 = np.zeros((0, B)); pl = np.zeros(B); G = np.ones((v.shape[0], 3))
+    renderer.renderStreamedGradient(o0, o0, v, f, 64, LB, UB, RES, T0, pl, G, T0, T0, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert (G == 1.0).all() and pl[1] > 0
+    # zero faces: transient zeroed, gradient untouched
+    o, n = scenes.wall_grid(2)
+    f0 = np.zeros((0, 3), np.int32); T = np.full((4, B), 5.0)
+    renderer.renderStreamedTransient(o, n, v, f0, 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert (T == 0).all()
+    # bad numBins / resolution are rejected by the C layer with a message
+    lib, h = gpu_ctx.lib, gpu_ctx.handle
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)); dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib.nlos_streamed_render_transient(h, fp(o), 4, fp(n), fp(v), 4, None, None, f.ctypes.data_as(C.POINTER(C.c_int)), 2, 64, 0.0, 1.44, 1.2e-3,
+                                            dp(T), dp(pl), 1, 1, 0)
+    assert rc == nb._ffi.NLOS_ERR_INVALID and b'numBins' in lib.nlos_last_error(h)
+    rc = lib.nlos_streamed_render_transient(h, fp(o), 4, fp(n), fp(v), 4, None, None, f.ctypes.data_as(C.POINTER(C.c_int)), 2, 64, 0.0, 1.44, 0.0,
+                                            dp(T), dp(pl), 1, 1, B)
+    assert rc == nb._ffi.NLOS_ERR_INVALID
+    assert lib.nlos_streamed_render_transient(None, fp(o), 4, fp(n), fp(v), 4, None, None, f.ctypes.data_as(C.POINTER(C.c_int)), 2, 64, 0.0, 1.44, 1.2e-3,
+                                              dp(T), dp(pl), 1, 1, B) == nb._ffi.NLOS_ERR_INVALID
+    # the context still works afterwards
+    renderer.renderStreamedTransient(o, n, v, f, 64, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert T.sum() > 0
+
+
+@pytest.mark.parametrize('spp', [3, 40])
+def test_many_samples_per_triangle(spp, oracle, gpu_ctx):
+    """spp > 1 (odd and even sample indices share a Philox block), forward + gradient + smoothed forward."""
+    from nlos_surface_optimization_b200 import renderer, scenes
+    v, f = scenes.icosphere(2, 0.1, (0.0, 0.01, 0.45), noise=0.03, seed=9); o, n = scenes.wall_grid(3)
+    ns = spp * f.shape[0]
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT and rel_l2(G, G_ref) <= TOL_GRADIENT
+    Ts_ref = oracle.transient(o, n, v, f, ns, LB, UB, RES, 10, 2)[0]
+    Ts = np.zeros_like(T)
+    renderer.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, Ts, pl, 10, 2, ctx=gpu_ctx)
+    assert rel_l2(Ts, Ts_ref) <= TOL_TRANSIENT
