@@ -320,16 +320,26 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
   double g1x = 0, g1y = 0, g1z = 0, g2x = 0, g2y = 0, g2z = 0, g3x = 0, g3y = 0, g3z = 0, gs = 0;
   f3 e1, e2, e3;
   if (active) { e1 = t.st.v3 - t.st.v2; e2 = t.st.v1 - t.st.v3; e3 = t.st.v2 - t.st.v1; }
-  for (int64_t s = s0; s < s1; ++s) {
-    const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
-    const f3 o = xyz(o4), on = xyz(n4);
-    for (int k = 0; k < P.spp; ++k) {
+  // slots (source*spp + k) are walked in groups of 32: lane l fetches the visibility word of slot base+l in ONE strided load
+  // (32 independent L2 accesses in flight) and the words are then broadcast by shuffle, instead of one dependent L2 round trip
+  // per slot at the top of the loop body.
+  const int64_t slotA = s0 * P.spp, slotB = s1 * P.spp;
+  for (int64_t base = slotA; base < slotB; base += 32) {
+    unsigned myword = 0u;
+    if (USE_VIS) {
+      const int64_t sl = base + lane;
+      if (sl < slotB && warp_global * 32 < sc.F) myword = __ldg(vis + (size_t)sl * P.words_per_row + warp_global);
+    }
+    const int cnt = (int)(slotB - base < 32 ? slotB - base : 32);
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t slot = base + i;
+      const int64_t s = P.spp == 1 ? slot : slot / P.spp;
+      const int k = P.spp == 1 ? 0 : (int)(slot - s * P.spp);
       bool bit = active;
-      if (USE_VIS) {
-        const unsigned m = warp_global * 32 < sc.F ? __ldg(vis + ((size_t)s * P.spp + k) * P.words_per_row + warp_global) : 0u;
-        bit = active && ((m >> lane) & 1u);
-      }
+      if (USE_VIS) { const unsigned m = __shfl_sync(0xffffffffu, myword, i); bit = active && ((m >> lane) & 1u); }
       if (!bit) continue;
+      const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
+      const f3 o = xyz(o4), on = xyz(n4);
       SampleGeom g;
       if (!sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) continue;
       if (!(g.r <= ub_half && g.r >= lb_half)) continue;
