@@ -1,8 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/nlos_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package never imports this module.  PARITY UNPINNED: see the header
-of nlos_oracle.cpp.
+--impl reference legs.  The product package never imports this module.  PARITY: pinned statistically to the reference's
+own code (oracle/_ref, tests/test_reference_pin.py), not bit-pinned: see the header of nlos_oracle.cpp.
 """
 import ctypes as C
 import math

@@ -1,0 +1,177 @@
+"""Case table shared by tools/make_ref_fixtures.py (runs the REFERENCE's own code, oracle/_ref) and tests/test_reference_pin.py
+(runs the oracle and, on a GPU, the CUDA path on the same inputs).  Every case is a small seeded scene; stochastic outputs are
+compared statistically (the reference's Mersenne-Twister sample stream is unrelated to the counter-based one used here), deterministic
+ones (regularisers, ray queries) directly.
+
+Scenes avoid the places where the reference itself is undefined (found while pinning):
+  * render_intensity adds into intensity[triangle] from all workers unsynchronised  -> reference run with one thread;
+  * streamed_render_normal_smoothing / _curvature_grad assign (not add) per vertex and then sum per-thread buffers, so the result depends
+    on how triangles fall on threads                                               -> reference run with one thread (= serial order);
+  * render_smoothed_vertex_gradients allocates 3*numBins per thread but clears 3*numVertices (transient_and_gradient.cpp:401,406)
+                                                                                     -> case built with numVertices == numBins;
+  * ggx evalNWDiff leaves its outputs unset when n.w <= 0 (ggx_confocal.cpp:138-166), NaN with shading normals on silhouettes
+                                                                                     -> GGX + shading gradient pinned on a height field;
+  * the gradient tap loop reads difference[source*numBins + bin] for bin >= numBins when a sample sits within 2*sigma_bin bins of the
+    upper bound (transient_and_gradient.cpp:685-690, no range check)                 -> every scene keeps 2r + 2 bins below the upper bound.
+"""
+import numpy as np
+from nlos_surface_optimization_b200 import scenes
+
+LB, UB = 0.0, 1.44
+RES = 4.8e-3                      # 300 bins
+RES_VG = 0.0089                   # 162 bins == V of icosphere(2)
+
+
+def wall():
+    return scenes.wall_grid(4)
+
+
+def ico():
+    return scenes.icosphere(1, 0.12, (0.03, -0.02, 0.45), noise=0.05, seed=3)       # V=42 F=80, back half self-occluded
+
+
+def ico2():
+    return scenes.icosphere(2, 0.12, (0.03, -0.02, 0.45), noise=0.03, seed=3)       # V=162 F=320
+
+
+def field():
+    v, f = scenes.heightfield(6)                                                      # V=36 F=50
+    v[:, 2] = 0.45 + 0.25 * (v[:, 2] - 0.45)                                          # gentle slopes: n.w > 0 for every wall point
+    v[:, :2] *= 0.5                                                                   # 2r + 2 bins < upper bound (see below)
+    return np.ascontiguousarray(v), f
+
+
+def occluder():
+    """bumpy sphere partly hidden behind a quad: visibility against OTHER geometry, not only self-occlusion."""
+    return scenes.merge([ico(), scenes.quad(0.3, 0.05, 0.02, 0.0)])
+
+
+def albedo(v):
+    return (0.5 + np.random.RandomState(0).rand(v.shape[0])).astype(np.float32)
+
+
+def jitter_kernel():
+    x = np.arange(21) - 8.0
+    jw = np.exp(-0.5 * (x / 3.0) ** 2) * (1 + 0.3 * np.sin(x)); jw /= jw.sum()
+    return jw, np.gradient(jw)
+
+
+def target(oracle, v, f, num_sample, res=RES, **kw):
+    """ground-truth transient = the oracle's render of the mesh pushed back by 1 cm (deterministic: fixed seed)."""
+    o, n = wall()
+    v2 = v.copy(); v2[:, 2] += 0.01
+    return oracle.transient(o, n, v2, f, num_sample, LB, UB, res, 10, 1, seed=5, **kw)[0]
+
+
+# name -> dict(kind, scene, samples, kwargs).  kinds: transient, intensity, gradient (T and G), scalar (albedo / alpha derivative),
+# vertex_gradient, jitter_transient, jitter_gradient
+S = 400000
+CASES = {
+    'transient_r10_s1':     dict(kind='transient', scene='ico', S=S, rs=10, sb=1),
+    'transient_r1_s1':      dict(kind='transient', scene='ico', S=S, rs=1, sb=1),
+    'transient_r4_s2':      dict(kind='transient', scene='ico', S=S, rs=4, sb=2),
+    'transient_occluder':   dict(kind='transient', scene='occluder', S=S, rs=10, sb=1),
+    'transient_shading':    dict(kind='transient', scene='ico', S=S, rs=10, sb=1, shading=True),
+    'transient_albedo':     dict(kind='transient', scene='ico', S=S, rs=10, sb=1, albedo=True),
+    'intensity':            dict(kind='intensity', scene='ico', S=S),
+    'gradient_t1_l0':       dict(kind='gradient', scene='ico', S=S, rs=10, sb=1, tf=1, lf=0),
+    'gradient_t1_l1':       dict(kind='gradient', scene='ico', S=S, rs=10, sb=1, tf=1, lf=1),
+    'gradient_t0_l0':       dict(kind='gradient', scene='ico', S=S, rs=4, sb=2, tf=0, lf=0),
+    'gradient_occluder':    dict(kind='gradient', scene='occluder', S=S, rs=10, sb=1, tf=1, lf=0),
+    'gradient_shading':     dict(kind='gradient', scene='ico', S=S, rs=10, sb=1, tf=1, lf=0, shading=True),
+    'gradient_w_albedo':    dict(kind='gradient', scene='ico', S=S, rs=10, sb=1, tf=1, lf=0, albedo=True),
+    'gradient_albedo':      dict(kind='scalar', scene='ico', S=S, rs=10, sb=1, albedo=True),
+    'ggx_transient_a03':    dict(kind='transient', scene='ico', S=S, rs=10, sb=1, alpha=0.3),
+    'ggx_transient_a08_sh': dict(kind='transient', scene='ico', S=S, rs=10, sb=1, alpha=0.8, shading=True),
+    'ggx_intensity':        dict(kind='intensity', scene='ico', S=S, alpha=0.5),
+    'ggx_gradient_a03':     dict(kind='gradient', scene='ico', S=S, rs=10, sb=1, tf=1, lf=0, alpha=0.3),
+    'ggx_gradient_field_sh': dict(kind='gradient', scene='field', S=S, rs=10, sb=1, tf=1, lf=0, alpha=0.5, shading=True),
+    'ggx_gradient_alpha':   dict(kind='scalar', scene='ico', S=S, rs=10, sb=1, alpha=0.5),
+    'vertex_gradient_v20':  dict(kind='vertex_gradient', scene='ico2', S=S, rs=10, sb=1, vertex=20),
+    'vertex_gradient_v100': dict(kind='vertex_gradient', scene='ico2', S=S, rs=10, sb=1, vertex=100),
+    'jitter_transient':     dict(kind='jitter_transient', scene='ico', S=S, offset=8),
+    'jitter_transient_sh':  dict(kind='jitter_transient', scene='ico', S=S, offset=8, shading=True),
+    'jitter_gradient_t1':   dict(kind='jitter_gradient', scene='ico', S=S, offset=8, tf=1),
+    'jitter_gradient_t0':   dict(kind='jitter_gradient', scene='occluder', S=S, offset=8, tf=0),
+}
+SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder}
+
+
+def run_case(impl, oracle, c, seed=None, relabel=None):
+    """Run one case on `impl` (oracle / reference / gpu adapter: same function names as oracle.oracle).  `seed` is passed where the
+    implementation takes one; `relabel` = (source permutation, face permutation) renders a relabelled copy of the same scene (how
+    independent draws are obtained from the reference, whose seed is fixed) and un-permutes the outputs.  Returns a dict of arrays."""
+    o, n = wall(); v, f = SCENES[c['scene']]()
+    kw = {}
+    if seed is not None:
+        kw['seed'] = seed
+    vn = scenes.vertex_normals(v, f) if c.get('shading') else None
+    va = albedo(v) if c.get('albedo') else None
+    sp = np.arange(o.shape[0]); fp = np.arange(f.shape[0])
+    if relabel is not None:
+        sp, fp = relabel
+    o_, n_, f_ = o[sp], n[sp], f[fp]
+    inv_s = np.argsort(sp); inv_f = np.argsort(fp)
+    alpha = c.get('alpha')
+    akw = {} if alpha is None else {'alpha': alpha}
+    k = c['kind']
+    if k == 'transient':
+        T = impl.transient(o_, n_, v, f_, c['S'], LB, UB, RES, c['rs'], c['sb'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)[0]
+        return {'T': T[inv_s]}
+    if k == 'intensity':
+        I = impl.intensity(o_, n_, v, f_, c['S'], LB, UB, vertex_normal=vn, **akw, **kw)
+        return {'I': I[inv_f]}
+    if k in ('gradient', 'scalar'):
+        tkw = dict(akw)
+        if va is not None:
+            tkw['vertex_albedo'] = va
+        if vn is not None:
+            tkw['vertex_normal'] = vn
+        data = target(oracle, v, f, c['S'], **tkw); w = np.ones_like(data)
+        if k == 'gradient':
+            T, G, _ = impl.gradient(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], c['tf'], c['lf'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)
+            return {'T': T[inv_s], 'G': G}
+        if alpha is None:
+            T, g = impl.gradient_albedo(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], va, **kw)
+        else:
+            T, g = impl.gradient_alpha(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], alpha, **kw)
+        return {'g': np.array([g])}
+    if k == 'vertex_gradient':
+        G = impl.vertex_gradient(c['vertex'], o[:1], n[:1], v, f_, c['S'], LB, UB, RES_VG, c['rs'], c['sb'], **kw)
+        return {'VG': np.asarray(G).reshape(-1, 3)}
+    jw, jg = jitter_kernel()
+    if k == 'jitter_transient':
+        T = impl.jitter_transient(o_, n_, v, f_, c['S'], LB, UB, RES, jw, c['offset'], vertex_normal=vn, **kw)[0]
+        return {'T': T[inv_s]}
+    if k == 'jitter_gradient':
+        v2 = v.copy(); v2[:, 2] += 0.01
+        data = oracle.jitter_transient(o, n, v2, f, c['S'], LB, UB, RES, jw, c['offset'], seed=5)[0]; w = np.ones_like(data)
+        T, G, _ = impl.jitter_gradient(o_, n_, v, f_, c['S'], LB, UB, RES, jw, jg, c['offset'], data[sp], w, c['tf'], **kw)
+        return {'T': T[inv_s], 'G': G}
+    raise KeyError(k)
+
+
+class OracleAdapter(object):
+    """oracle.oracle with the albedo / alpha scalar derivatives under the reference's names."""
+    def __init__(self, oracle):
+        self.o = oracle
+        for name in ('transient', 'intensity', 'gradient', 'vertex_gradient', 'jitter_transient', 'jitter_gradient'):
+            setattr(self, name, getattr(oracle, name))
+
+    def gradient_albedo(self, o, n, v, f, S, lb, ub, res, data, w, rs, sb, va, seed=None):
+        return self.o.gradient(o, n, v, f, S, lb, ub, res, data, w, rs, sb, 1, 0, vertex_albedo=va, kind=1, **({} if seed is None else {'seed': seed}))
+
+    def gradient_alpha(self, o, n, v, f, S, lb, ub, res, data, w, rs, sb, alpha, seed=None):
+        return self.o.gradient(o, n, v, f, S, lb, ub, res, data, w, rs, sb, 1, 0, alpha=alpha, kind=2, **({} if seed is None else {'seed': seed}))
+
+
+def two_sample_z(mean_a, std_a, n_a, mean_b, std_b, n_b):
+    """Two-sample z per element with the pooled standard deviation (both sides are the same estimator with the same sample count, so
+    their per-element variances are equal; pooling keeps z well behaved when one side has few draws).  Elements without spread on
+    either side are skipped.  Returns (z, relative L2 distance of the means)."""
+    pooled = np.sqrt(((n_a - 1) * std_a ** 2 + (n_b - 1) * std_b ** 2) / (n_a + n_b - 2))
+    se = pooled * np.sqrt(1.0 / n_a + 1.0 / n_b)
+    ok = se > 0
+    z = (mean_a[ok] - mean_b[ok]) / se[ok]
+    rel = np.linalg.norm(mean_a - mean_b) / max(np.linalg.norm(mean_b), 1e-300)
+    return z, rel

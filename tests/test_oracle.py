@@ -1,7 +1,7 @@
 """CPU tests of the oracle itself (oracle/nlos_oracle.cpp): known-answer RNG vectors, closed-form renders,
 brute-force-vs-BVH agreement, smoothing conservation, finite differences, and the committed golden fixtures.
-PARITY UNPINNED against the reference (it ships no golden vectors and cannot be built here) — these tests pin
-the oracle against mathematics instead."""
+These tests pin the oracle against mathematics; tests/test_reference_pin.py pins it (statistically) against the
+reference's own code compiled with stand-in library headers (oracle/_ref)."""
 import os
 import numpy as np
 import pytest
