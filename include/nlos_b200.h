@@ -172,6 +172,32 @@ int nlos_jitter_streamed_render_gradient(nlos_ctx* ctx, const double* data, cons
                                          int weight_offset, int weight_length, double* transient, double* pathlengths,
                                          double* gradient, int testing_flag, int numBins);
 
+/* ---- first-generation module `renderer` (stratified_transient_raytracer/), SURVEY.md 8f row N4 ------------------ */
+
+/* stratified_transient_raytracer/stratifiedStreamedTransientRenderer.h  streamed_render_transient (renderer.pyx:36-88):
+ * raw histogram (no temporal smoothing); the form factor is NOT clamped (stratifiedStreamedTransientRenderer.cpp:130-137),
+ * so a visible back-facing sample contributes ff^2 */
+int nlos_sr_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD,
+                                      const float* verticesD, int numVertices, const float* vertexNormal /*nullable*/,
+                                      const float* vertexAlbedo /*nullable*/, const int* trianglesD, int numTriangles,
+                                      int numSamples, float pathlengthLowerBound, float pathlengthUpperBound,
+                                      float pathlengthResolution, double* transient, double* pathlengths, int numBins);
+/* stratified_transient_raytracer/stratifiedTransientRenderer.h  render_transient (renderer.pyx:93-102): one origin,
+ * originD[3], normalD[3], transient[numBins] */
+int nlos_sr_render_transient(nlos_ctx* ctx, const float* originD, const float* normalD, const float* verticesD,
+                             int numVertices, const int* trianglesD, int numTriangles, int numSamples,
+                             float pathlengthLowerBound, float pathlengthUpperBound, float pathlengthResolution,
+                             double* transient, double* pathlengths, int numBins);
+/* stratified_transient_raytracer/stratifiedStreamedGradientRenderer.h  streamed_render_gradient (renderer.pyx:22-34):
+ * difference = data - transient, box-filtered twice with half-width w_width (stratifiedStreamedGradientRenderer.cpp:447-458);
+ * one tap per sample, normal-variation term always included (:266-271); gradient is OVERWRITTEN (:414), not accumulated.
+ * The reference's output-index slips (:278, :290-291) are not reproduced. */
+int nlos_sr_streamed_render_gradient(nlos_ctx* ctx, const double* data, const float* originD, int measurement,
+                                     const float* normalD, const float* verticesD, int numVertices, const int* trianglesD,
+                                     int numTriangles, int numSamples, float pathlengthLowerBound,
+                                     float pathlengthUpperBound, float pathlengthResolution, int w_width, double* transient,
+                                     double* pathlengths, double* gradient, int numBins);
+
 /* ---- module `embree_intersector` (embree_intersector/), SURVEY.md 8f row N2 ---------------------------- */
 
 /* embree_intersector/c_embree_intersector.h:8  embree3_tbb_line_intersection (embree_intersector.pyx:92):

@@ -15,7 +15,7 @@ __version__ = '0.1.0'
 
 def __getattr__(name):
     # lazy submodules keep `import nlos_surface_optimization_b200` cheap and free of side effects
-    if name in ('renderer', 'ggx', 'rendering', 'scenes', 'dist', 'embree_intersector', 'jitter'):
+    if name in ('renderer', 'ggx', 'rendering', 'scenes', 'dist', 'embree_intersector', 'jitter', 'renderer_sr'):
         import importlib
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -63,6 +63,10 @@ SIGNATURES = {
                                                         _d, C.c_int, C.c_int, _d, _d, C.c_int]),
     'nlos_jitter_streamed_render_gradient': (C.c_int, [_ctx, _d, _d, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                                        _d, _d, C.c_int, C.c_int, _d, _d, _d, C.c_int, C.c_int]),
+    'nlos_sr_streamed_render_transient': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _d, _d, C.c_int]),
+    'nlos_sr_render_transient': (C.c_int, [_ctx, _f, _f, _f, C.c_int, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _d, _d, C.c_int]),
+    'nlos_sr_streamed_render_gradient': (C.c_int, [_ctx, _d, _f, C.c_int, _f, _f, C.c_int, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                   _d, _d, _d, C.c_int]),
     'nlos_embree3_tbb_line_intersection': (C.c_int, [_ctx, _f, _f, C.c_int, _f, C.c_int, _i, C.c_int, _f]),
     'nlos_embree3_tbb_short_line_intersection': (C.c_int, [_ctx, _f, _f, C.c_int, _f, C.c_int, _i, C.c_int, _f]),
     'nlos_barycentric_to_world': (C.c_int, [_ctx, _f, C.c_int, _i, C.c_int, _f, C.c_int, _f]),

@@ -100,6 +100,7 @@ struct Job {
   double* scalar_out = nullptr;
   int kind = -1;   // -1 forward only, 0 vertex gradient, 1 albedo scalar, 2 alpha scalar, 3 intensity
   const double* jw = nullptr; const double* jg = nullptr; int joff = 0, jlen = 0;   // jitter/ temporal kernel (jlen > 0)
+  int sr = 0, w_width = 0;   // first-generation API (stratified_transient_raytracer/): unclamped forward, box-filtered residual, one tap, '=' into gradient
 };
 
 int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
@@ -114,7 +115,13 @@ int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
 // forward kernel: sample slots (source*spp + k) per warp pass, bounded by the visibility tile in shared memory
 int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 64; return std::min(std::max(c, 1), 256); }
 
-void run_job(Ctx& cx, const Job& j) {
+void run_job(Ctx& cx, const Job& j_in) {
+  Job j = j_in;
+  if (j.sr && j.kind == 0) {
+    // the first-generation gradient is the tabulated-kernel path with the unit kernel: A[b] = -2 diff[b], B[b] = 0
+    static const double kOne = 1.0, kZero = 0.0;
+    j.jw = &kOne; j.jg = &kZero; j.jlen = 1; j.joff = 0; j.refine = 1; j.sigma = 1;
+  }
   NLOS_CUDA_OK(cudaSetDevice(cx.device));
   NLOS_REQUIRE(j.L >= 0 && j.V >= 0 && j.F >= 0, "negative size");
   NLOS_REQUIRE(j.L == 0 || (j.origin && j.onormal), "origin/normal is null");
@@ -125,7 +132,8 @@ void run_job(Ctx& cx, const Job& j) {
     NLOS_REQUIRE(j.refine >= 1 && j.sigma >= 1, "refine_scale and sigma_bin must be >= 1");
     NLOS_REQUIRE(j.transient != nullptr, "transient is null");
   }
-  if (j.kind >= 0 && j.kind <= 2) NLOS_REQUIRE(j.data && j.weight, "data/weight is null");
+  if (j.kind >= 0 && j.kind <= 2) NLOS_REQUIRE(j.data && (j.weight || j.sr), "data/weight is null");
+  if (j.sr) NLOS_REQUIRE(j.w_width >= 0 && j.kind <= 0 && !j.ggx, "first-generation API: w_width must be >= 0");
   if (j.kind == 0) NLOS_REQUIRE(j.gradient != nullptr, "gradient is null");
   if (j.kind == 3) NLOS_REQUIRE(j.intensity != nullptr, "intensity is null");
 
@@ -177,7 +185,7 @@ void run_job(Ctx& cx, const Job& j) {
     P.r_fwd = (j.kind >= 0 && j.kind <= 2) ? (j.sigma < 5 ? 1 : j.refine) : j.refine;   // SSG.cpp:521-524
     if (j.kind == 3 || j.jlen > 0) P.r_fwd = 1;                                          // jitter: coarse histogram, then tabulated conv
     P.res_fwd = j.res / P.r_fwd;                                                         // TG.cpp:313
-    P.alpha = j.alpha; P.testing_flag = j.testing_flag;
+    P.alpha = j.alpha; P.testing_flag = j.testing_flag; P.sr = j.sr;
     P.words_per_row = (j.F + 31) / 32;
     TapTables taps;
     if (j.kind != 3) {
@@ -221,11 +229,16 @@ void run_job(Ctx& cx, const Job& j) {
         // ---- K3: residual
         // host data/weight ride the copy stream while the forward kernel (already enqueued) runs
         const double* d_data = stage_in(cx, "in_data", j.data, LB, cx.copy_stream);
-        const double* d_weight = stage_in(cx, "in_weight", j.weight, LB, cx.copy_stream);
+        const double* d_weight = j.weight ? stage_in(cx, "in_weight", j.weight, LB, cx.copy_stream) : nullptr;
         NLOS_CUDA_OK(cudaEventRecord(cx.ev_copy, cx.copy_stream));
         NLOS_CUDA_OK(cudaStreamWaitEvent(st, cx.ev_copy, 0));
         double* diff = cx.buf("diff").as<double>(LB);
         launch_residual(cx, d_data, d_weight, o_T.dev, diff, LB, j.loss_flag);
+        if (j.sr && j.w_width > 0) {                                                      // SR/SSG.cpp:447-458: box mean twice
+          double* tmp = cx.buf("diff_tmp").as<double>(LB);
+          launch_box_filter(cx, diff, tmp, j.numBins, j.L, j.w_width);
+          launch_box_filter(cx, tmp, diff, j.numBins, j.L, j.w_width);
+        }
         if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st));
         // ---- K4/K5: gradient
         P.chunk = auto_chunk(cx, "chunk_gradient", j.F, j.L, cx.chunk_gradient > 0 ? cx.chunk_gradient : 128);
@@ -240,6 +253,7 @@ void run_job(Ctx& cx, const Job& j) {
           double* acc = cx.buf("grad_acc").as<double>(3 * (size_t)j.V);
           NLOS_CUDA_OK(cudaMemsetAsync(acc, 0, 3 * (size_t)j.V * sizeof(double), st));
           launch_gradient(cx, sc, P, j.ggx, 0, diff, vis, d_wprefix, d_dprefix, acc);
+          if (j.sr) NLOS_CUDA_OK(cudaMemsetAsync(o_G.dev, 0, 3 * (size_t)j.V * sizeof(double), st));   // SR/SSG.cpp:414: cleared, not accumulated
           launch_finalize_gradient(cx, acc, o_G.dev, 3 * (size_t)j.V, 1.0 / (double)Lnorm);
         } else {
           double* acc = cx.buf("scalar_acc").as<double>(1);
@@ -563,6 +577,27 @@ static int run_ray_query(nlos_ctx* ctx, int mode, const float* originsD, const f
     return NLOS_OK;
   } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
   catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
+// ---- first-generation API (stratified_transient_raytracer/)
+int nlos_sr_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD, const float* verticesD, int numVertices,
+                                      const float* vertexNormal, const float* vertexAlbedo, const int* trianglesD, int numTriangles, int numSamples,
+                                      float lb, float ub, float res, double* transient, double* pathlengths, int numBins) {
+  Job j = base_job(originD, numSources, normalD, verticesD, numVertices, vertexNormal, vertexAlbedo, trianglesD, numTriangles, numSamples, lb, ub, res, numBins, 1, 1);
+  j.transient = transient; j.pathlengths = pathlengths; j.kind = -1; j.sr = 1;
+  return guarded(ctx, j);
+}
+int nlos_sr_render_transient(nlos_ctx* ctx, const float* originD, const float* normalD, const float* verticesD, int numVertices, const int* trianglesD,
+                             int numTriangles, int numSamples, float lb, float ub, float res, double* transient, double* pathlengths, int numBins) {
+  return nlos_sr_streamed_render_transient(ctx, originD, 1, normalD, verticesD, numVertices, nullptr, nullptr, trianglesD, numTriangles, numSamples, lb, ub, res,
+                                           transient, pathlengths, numBins);
+}
+int nlos_sr_streamed_render_gradient(nlos_ctx* ctx, const double* data, const float* originD, int measurement, const float* normalD, const float* verticesD,
+                                     int numVertices, const int* trianglesD, int numTriangles, int numSamples, float lb, float ub, float res, int w_width,
+                                     double* transient, double* pathlengths, double* gradient, int numBins) {
+  Job j = base_job(originD, measurement, normalD, verticesD, numVertices, nullptr, nullptr, trianglesD, numTriangles, numSamples, lb, ub, res, numBins, 1, 1);
+  j.data = data; j.weight = nullptr; j.transient = transient; j.pathlengths = pathlengths; j.gradient = gradient; j.kind = 0; j.sr = 1; j.w_width = w_width;
+  return guarded(ctx, j);
 }
 
 int nlos_embree3_tbb_line_intersection(nlos_ctx* ctx, const float* originsD, const float* directionsD, int num_ray, const float* verticesD, int num_vertices,

@@ -51,6 +51,8 @@ struct RenderParams {
   const double* jA;         // sum_i jitter_weight[i] * (-2) diff[s, b+i-offset]
   const double* jB;         // sum_i jitter_grad[i]   * (-2) diff[s, b+i-offset]
   double grad_coef;         // factor of the kernel-derivative term: 2/sigma^2 (Gaussian) or -2/res (jitter/TG.cpp:950)
+  int sr;                   // 1: first-generation renderer (stratified_transient_raytracer/): forward without the form-factor clamp
+                            //    (SR/SST.cpp:130-137), gradient with the normal-variation term always on (SR/SSG.cpp:266-271)
 };
 
 struct Status { int code = 0; std::string msg; };

@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
     int gen = 0, qhead = 0, qcount = 0;
     // per-lane traversal state of the ray in flight (cur == kSentinel: lane is idle)
     int cur = kSentinel, sp = 0, stack[kStack];
+#ifdef NLOS_TOPCACHE
+    int top = kDone;      // top of the traversal stack lives in a register: a pop uses it at once and the refill load is off the critical path
+#endif
 #if defined(NLOS_EXPERIMENT_EXTRALOAD) || defined(NLOS_EXPERIMENT_EXTRAALU)
     float sink = 0.f;
 #endif
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
             // it, so ff = -(n.d)(n_o.d)/r^2 < 0 and the sample adds nothing (TG.cpp:224-228).  The margins (1e-5 relative)
             // are far above float round-off; anything closer to edge-on goes through the full path.
             bool culled = false;
-            if (!HAS_VN) {
+            if (!HAS_VN && !P.sr) {
               const f3 w1 = t.st.v1 - o, w2 = t.st.v2 - o, w3 = t.st.v3 - o;
               const float m1 = 1e-5f * (fabsf(w1.x) + fabsf(w1.y) + fabsf(w1.z));
               culled = dot3(t.st.nf, w1) > m1 && dot3(on, w1) > m1 &&
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
             if (!culled && sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
               const f3 n = shading_normal<HAS_VN>(t, g);
               const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
-              if (ff > 0.0f) {                                                      // max(0,ff)==0 adds exactly 0 (TG.cpp:228)
+              if (P.sr ? ff != 0.0f : ff > 0.0f) {                                  // max(0,ff)==0 adds exactly 0 (TG.cpp:228); SR has no clamp
                 const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
                 float v = t.st.A * alb * ff * ff;
                 if (GGX) v = v * ggx_eval(P.alpha, dot3(n, -g.d));                  // ggx/TG.cpp:236-238
@@ -201,6 +204,9 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
           src = P.spp == 1 ? slot : slot / P.spp;
           ray = make_ray(xyz(__ldg(P.origin + src)), mk3(ws.dx[pos], ws.dy[pos], ws.dz[pos]));
           stack[0] = kDone; sp = 1; cur = sc.root_count > 0 ? leaf_ref(0, sc.root_count) : 0;
+#ifdef NLOS_TOPCACHE
+          top = kDone;
+#endif
         }
         const int prim_new = __shfl_sync(0xffffffffu, t.prim, (meta >> 16) & 31);
         if (fetch) prim = prim_new;
@@ -228,7 +234,20 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
         const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
-#ifndef NLOS_BRANCHY      // fully predicated child selection: no BSSY/BSYNC pair inside the step (measured 33.3 vs 35.8 ms)
+#if defined(NLOS_TOPCACHE)
+        {
+          const bool both = h0 && h1, any = h0 || h1, first0 = t0 <= t1;
+          const int nearr = (h0 && (!h1 || first0)) ? r0 : r1;
+          if (both) stack[sp] = top;
+          sp += both ? 1 : 0;
+          const int far = first0 ? r1 : r0;
+          cur = any ? nearr : top;
+          int below = top;
+          if (!any) below = stack[sp - 1];
+          sp -= any ? 0 : 1;
+          top = both ? far : below;
+        }
+#elif !defined(NLOS_BRANCHY)      // fully predicated child selection: no BSSY/BSYNC pair inside the step (measured 33.3 vs 35.8 ms)
         {
           const bool both = h0 && h1, any = h0 || h1, first0 = t0 <= t1;
           const int nearr = (h0 && (!h1 || first0)) ? r0 : r1;
@@ -253,7 +272,11 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         const int first = leaf_first(cur), cnt = leaf_count(cur);
         bool occ = false;
         for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes_fast(sc.ttris, first + j, ray, ts, prim);
+#ifdef NLOS_TOPCACHE
+        cur = occ ? kSentinel : top; top = stack[--sp];
+#else
         cur = occ ? kSentinel : stack[--sp];                     // occluded: drop the ray
+#endif
       }
       if (cur == kDone) {                                        // traversal finished without an occluder: visible
         const double dv = (double)val / (double)P.spp;           // TG.cpp:231-232
@@ -293,7 +316,18 @@ __global__ void k_residual(const double* __restrict__ data, const double* __rest
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double d = data[i] - T[i];
     if (loss_flag == 1) d = 2 * d * d * d;
-    diff[i] = d * weight[i];
+    diff[i] = weight ? d * weight[i] : d;
+  }
+}
+
+// centred (2w+1)-box mean of every residual row, zero padded and truncated to the row (one pass of SR/SSG.cpp:447-458; run twice)
+__global__ void k_box_filter(const double* __restrict__ in, double* __restrict__ out, int B, size_t n, int width) {
+  const double h = 1.0 / ((double)2 * width + 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i % (size_t)B); const double* row = in + (i - b);
+    double a = 0;
+    for (int j = 0; j <= 2 * width; ++j) { const int m = b + width - j; if (m >= 0 && m < B) a += h * row[m]; }
+    out[i] = a;
   }
 }
 
@@ -385,7 +419,7 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
           inten = alb * ff * ff;                                      // TG.cpp:950
           t1 = (2 * alb * c2 * c3) * (on * c3 - n * c2 + (4 * (-d)) * c2 * c3);   // :953
           t1 = t1 / hl5;                                              // :954
-          if (HAS_VN && P.testing_flag == 0) {                        // :959-964
+          if ((HAS_VN && P.testing_flag == 0) || P.sr) {              // :959-964; SR/SSG.cpp:266-271 always
             gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / hl4;
             const float ct = dot3(gn, n); gn = gn - n * ct;
           }
@@ -571,6 +605,12 @@ void launch_residual(Ctx& cx, const double* data, const double* weight, const do
   k_residual<<<blocks, 256, 0, cx.stream>>>(data, weight, T, diff, n, loss_flag);
   cx.launches += 1;
   NLOS_CUDA_OK(cudaGetLastError());
+}
+
+void launch_box_filter(Ctx& cx, const double* in, double* out, int B, int64_t L, int width) {
+  const size_t n = (size_t)L * B; if (n == 0) return;
+  k_box_filter<<<(int)std::min<size_t>((n + 255) / 256, 148 * 32), 256, 0, cx.stream>>>(in, out, B, n, width);
+  cx.launches += 1; NLOS_CUDA_OK(cudaGetLastError());
 }
 
 void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, int kind, const double* diff, const uint32_t* vis,

@@ -13,6 +13,7 @@ void launch_finalize_gradient(Ctx& cx, const double* acc, double* gradient, size
 void launch_visibility(Ctx& cx, const DeviceScene& sc, const RenderParams& P, uint8_t* vis_out, unsigned long long* counters);
 void launch_pack4(Ctx& cx, const float* in, float4* out, size_t n);
 void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res);
+void launch_box_filter(Ctx& cx, const double* in, double* out, int B, int64_t L, int width);
 void launch_jitter_conv(Ctx& cx, const double* H, const double* w, int J, int off, int B, int64_t L, double* T);
 void launch_jitter_tables(Ctx& cx, const double* diff, const double* w, const double* g, int J, int off, int B, int64_t L, double* jA, double* jB);
 // mesh_kernels.cu

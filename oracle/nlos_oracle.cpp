@@ -29,6 +29,7 @@
 //   per-bin vertex grad   smoothed_transient/transient_and_gradient.cpp:379-439, 697-840
 //   mesh regularisers     smoothed_transient/stratifiedStreamedGradientRenderer.cpp:27-180
 //   GGX BRDF              ggx/ggx_confocal.cpp:13-231
+//   first generation (SR) stratified_transient_raytracer/stratifiedStreamedTransientRenderer.cpp:26-142, ...GradientRenderer.cpp:157-296, 395-487
 //   bits -> float         smoothed_transient/rng_sse.h:33-42
 //
 // Deliberate, documented departures (SURVEY.md A.6 "F" rows):
@@ -307,6 +308,7 @@ struct Params {
   float alpha;        // < 0 => Lambertian (smoothed_transient/), >= 0 => GGX (ggx/)
   int num_samples; float lb, ub, res; int numBins;
   uint64_t seed;
+  bool sr = false;    // first-generation renderer (stratified_transient_raytracer/): forward without the form-factor clamp
 };
 static inline int spp_of(const Params& p) { return 1 + (p.num_samples - 1) / p.F; }   // TG.cpp:289
 
@@ -384,7 +386,7 @@ static void render_transients(const Scene& sc, const Params& p, int r, int s, do
         if (!sm.visible || !sm.in_range) continue;
         V3 n = shading_normal(p, ts, sm); float alb = shading_albedo(p, ts, sm);
         float ff = -dot3(n, sm.d) * dot3(o_n, sm.d) / sm.r / sm.r;     // :224-227
-        ff = std::max(0.0f, ff);                                    // :228 (clamps the product)
+        if (!p.sr) ff = std::max(0.0f, ff);                         // :228 (clamps the product); SR/SST.cpp:130-137 has no clamp
         int64_t bin = (int64_t)floorf((2.0f * sm.r - p.lb) / res_eff);   // :229
         if (bin < 0 || bin >= nbf) continue;                        // reference: out-of-bounds write
         float val = ts.A * alb * ff * ff;
@@ -493,6 +495,65 @@ static void render_gradients(const Scene& sc, const Params& p, int r, int s, con
     }
   }
   for (int t = 0; t < nth; ++t) for (size_t d = 0; d < G; ++d) gradient[d] += accs[(size_t)t * G + d] / (double)p.L;   // :561-565 ('+=' into caller's array)
+}
+
+// ---------------------------------------------------------------- first-generation renderer (stratified_transient_raytracer/, "SR")
+// residual of SR/SSG.cpp:436-462: difference = data - transient, then (w_width > 0) two passes of a centred (2w+1)-box mean with
+// zero padding, each truncated to the numBins range (the reference convolves into a padded buffer and re-reads [w, w+numBins))
+static void sr_difference(const Params& p, const double* data, const double* transient, int width, std::vector<double>& diff) {
+  const int B = p.numBins; diff.resize((size_t)p.L * B);
+  for (size_t i = 0; i < diff.size(); ++i) diff[i] = data[i] - transient[i];
+  if (width <= 0) return;
+  const double h = 1.0 / ((double)2 * width + 1);
+  std::vector<double> tmp(B);
+  for (int64_t s = 0; s < p.L; ++s) {
+    double* row = diff.data() + s * B;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int b = 0; b < B; ++b) { double a = 0; for (int j = 0; j <= 2 * width; ++j) { int m = b + width - j; if (m >= 0 && m < B) a += h * row[m]; } tmp[b] = a; }
+      std::copy(tmp.begin(), tmp.end(), row);
+    }
+  }
+}
+// gradient task of SR/SSG.cpp:157-296: one tap, weight 1, no kernel-derivative term, the normal-variation term gn ALWAYS included
+// (face normals).  typos != 0 reproduces the reference's output-index slips (:278 v1.z added into v1.y; :290-291 v3.y -> slot +2,
+// v3.z -> slot +3) so that the arithmetic can be pinned against the reference's own code; the product implements typos == 0.
+static void render_gradients_sr(const Scene& sc, const Params& p, const double* diff, double* gradient, int typos) {
+  const int spp = spp_of(p); const int B = p.numBins; const size_t G = (size_t)3 * p.V;
+  std::vector<double> acc(G + 4, 0.0);
+  for (int64_t src = 0; src < p.L; ++src) {
+    V3 o_n = ld3(p.onormal, src);
+    for (int f = 0; f < p.F; ++f) {
+      TriSetup ts = setup_tri(p, f);
+      for (int k = 0; k < spp; ++k) {
+        Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
+        if (!sm.visible || !sm.in_range) continue;
+        V3 n = ts.nf; V3 d = sm.d; float hl = sm.r;
+        float c2 = dot3(o_n, d), c3 = dot3(n, -d);
+        if (c2 < 0) c2 = 0; if (c3 < 0) c3 = 0;
+        float ff = c2 * c3 / hl / hl;
+        int64_t bin = (int64_t)floorf((2.0f * hl - p.lb) / p.res);
+        if (bin < 0 || bin >= B) continue;                           // reference: out-of-bounds read
+        double intensity = 1.0f * ff * ff;
+        V3 t1 = (2 * c2 * c3) * (o_n * c3 - n * c2 + (4 * (-d)) * c2 * c3);
+        t1 = t1 / powf(hl, 5);
+        V3 t2 = n * (float)intensity;
+        V3 gn = (-2 * d) * c3 * c2 * c2; gn = gn / powf(hl, 4);
+        float ct = dot3(gn, n); gn = gn - n * ct;
+        t2 = (t2 + gn) / (2 * ts.A);
+        const float df = (float)((-2) * diff[src * B + bin]);
+        V3 g;
+        g = t1 * sm.u + cross3(t2, ts.v3 - ts.v2); g = g * df;
+        acc[3 * ts.i1] += (double)(ts.A * g.x) / (double)spp; acc[3 * ts.i1 + 1] += (double)(ts.A * g.y) / (double)spp;
+        acc[3 * ts.i1 + (typos ? 1 : 2)] += (double)(ts.A * g.z) / (double)spp;
+        g = t1 * sm.v + cross3(t2, ts.v1 - ts.v3); g = g * df;
+        acc[3 * ts.i2] += (double)(ts.A * g.x) / (double)spp; acc[3 * ts.i2 + 1] += (double)(ts.A * g.y) / (double)spp; acc[3 * ts.i2 + 2] += (double)(ts.A * g.z) / (double)spp;
+        g = t1 * sm.w + cross3(t2, ts.v2 - ts.v1); g = g * df;
+        acc[3 * ts.i3] += (double)(ts.A * g.x) / (double)spp;
+        acc[3 * ts.i3 + (typos ? 2 : 1)] += (double)(ts.A * g.y) / (double)spp; acc[3 * ts.i3 + (typos ? 3 : 2)] += (double)(ts.A * g.z) / (double)spp;
+      }
+    }
+  }
+  for (size_t d = 0; d < G; ++d) gradient[d] = acc[d] / (double)p.L;   // SR/SSG.cpp:414, 476-480: cleared, then summed ('=' semantics)
 }
 
 // scalar gradients: albedo (TG.cpp:571-695, 441-503) and GGX alpha (ggx/TG.cpp:385-512, 514-577)
@@ -626,6 +687,30 @@ int nlos_oracle_gradient(const double* data, const double* weight, const float* 
   std::vector<double> diff; make_difference(p, data, weight, transient, loss_flag, diff);
   if (kind == 0) render_gradients(sc, p, refine_scale, sigma_bin, diff.data(), gradient, testing_flag);
   else { double g = render_scalar_gradient(sc, p, refine_scale, sigma_bin, diff.data(), kind == 2); if (scalar_out) *scalar_out = g; }
+  return 0;
+}
+
+// ---- first-generation API (stratified_transient_raytracer/renderer.pyx:13-102)
+int nlos_oracle_sr_transient(const float* origin, int64_t L, const float* onormal, const float* verts, int V, const float* vnormal, const float* valbedo,
+                             const int32_t* faces, int F, int num_samples, float lb, float ub, float res, int numBins, double* transient, double* pathlengths,
+                             uint64_t seed, int64_t src_offset, int mode) {
+  Params p = make_params(origin, L, onormal, verts, V, vnormal, valbedo, faces, F, -1.f, num_samples, lb, ub, res, numBins, seed, src_offset);
+  p.sr = true;
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  render_transients(sc, p, 1, 1, transient, nullptr, nullptr);
+  return 0;
+}
+int nlos_oracle_sr_gradient(const double* data, const float* origin, int64_t L, const float* onormal, const float* verts, int V, const int32_t* faces, int F,
+                            int num_samples, float lb, float ub, float res, int numBins, int w_width, double* transient, double* pathlengths, double* gradient,
+                            uint64_t seed, int64_t src_offset, int mode, int typos) {
+  Params p = make_params(origin, L, onormal, verts, V, nullptr, nullptr, faces, F, -1.f, num_samples, lb, ub, res, numBins, seed, src_offset);
+  p.sr = true;
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, mode & 1);
+  fill_pathlengths(p, pathlengths);
+  render_transients(sc, p, 1, 1, transient, nullptr, nullptr);
+  std::vector<double> diff; sr_difference(p, data, transient, w_width, diff);
+  render_gradients_sr(sc, p, diff.data(), gradient, typos);
   return 0;
 }
 

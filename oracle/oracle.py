@@ -224,3 +224,31 @@ def jitter_gradient(origin, normal, vertices, faces, num_sample, lower, upper, r
                                       C.c_int(jitter_offset), C.c_int(jw.shape[0]), _p(T, C.c_double), _p(pl, C.c_double), _p(G, C.c_double),
                                       C.c_int(testing_flag), C.c_uint64(seed), C.c_int64(src_offset), C.c_int(1 if brute else 0))
     return T, G, pl
+
+
+def sr_transient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, vertex_normal=None, vertex_albedo=None, seed=DEFAULT_SEED,
+                 src_offset=0, brute=False):
+    """First-generation forward (stratified_transient_raytracer/): raw histogram, form factor NOT clamped."""
+    origin = _f32(origin).reshape(-1, 3); normal = _f32(normal).reshape(-1, 3); vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vn = None if vertex_normal is None else _f32(vertex_normal); va = None if vertex_albedo is None else _f32(vertex_albedo)
+    L, V, F = origin.shape[0], vertices.shape[0], faces.shape[0]; B = num_bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B)
+    lib().nlos_oracle_sr_transient(_p(origin, C.c_float), C.c_int64(L), _p(normal, C.c_float), _p(vertices, C.c_float), C.c_int(V), _p(vn, C.c_float),
+                                   _p(va, C.c_float), _p(faces, C.c_int32), C.c_int(F), C.c_int(num_sample), C.c_float(lower), C.c_float(upper),
+                                   C.c_float(resolution), C.c_int(B), _p(T, C.c_double), _p(pl, C.c_double), C.c_uint64(seed), C.c_int64(src_offset),
+                                   C.c_int(1 if brute else 0))
+    return T, pl
+
+
+def sr_gradient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, w_width, data, seed=DEFAULT_SEED, src_offset=0, brute=False,
+                typos=False):
+    """First-generation gradient: box-filtered residual, one tap, gn always.  typos=True reproduces the reference's index slips."""
+    origin = _f32(origin); normal = _f32(normal); vertices = _f32(vertices); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    L, V, F = origin.shape[0], vertices.shape[0], faces.shape[0]; B = num_bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((V, 3))
+    lib().nlos_oracle_sr_gradient(_p(data, C.c_double), _p(origin, C.c_float), C.c_int64(L), _p(normal, C.c_float), _p(vertices, C.c_float), C.c_int(V),
+                                  _p(faces, C.c_int32), C.c_int(F), C.c_int(num_sample), C.c_float(lower), C.c_float(upper), C.c_float(resolution), C.c_int(B),
+                                  C.c_int(w_width), _p(T, C.c_double), _p(pl, C.c_double), _p(G, C.c_double), C.c_uint64(seed), C.c_int64(src_offset),
+                                  C.c_int(1 if brute else 0), C.c_int(1 if typos else 0))
+    return T, G, pl

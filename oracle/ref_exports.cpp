@@ -1,13 +1,26 @@
 // TEST INFRASTRUCTURE.  extern "C" forwarding stubs over the reference's own (C++-linkage) entry points, so that tests can call the
 // reference's unmodified translation units (compiled by `make -C oracle ref` from /root/reference against oracle/ref_shim) via ctypes.
 // Compiled once per reference module: -DREF_RENDERER (smoothed_transient/), -DREF_GGX (ggx/), -DREF_JITTER (jitter/),
-// -DREF_INTERSECTOR (embree_intersector/).  The reference headers are found through -I<reference module dir>.
+// -DREF_INTERSECTOR (embree_intersector/), -DREF_SR (stratified_transient_raytracer/, the first-generation renderer).  The reference headers are found through -I<reference module dir>.
 #if defined(REF_INTERSECTOR)
 #include "c_embree_intersector.h"
 extern "C" {
 void ref_embree3_tbb_line_intersection(float* o, float* d, int n, float* v, int nv, int* f, int nf, float* out) { embree3_tbb_line_intersection(o, d, n, v, nv, f, nf, out); }
 void ref_embree3_tbb_short_line_intersection(float* o, float* d, int n, float* v, int nv, int* f, int nf, float* out) { embree3_tbb_short_line_intersection(o, d, n, v, nv, f, nf, out); }
 void ref_barycentric_to_world(float* v, int* f, float* bary, int n, float* world) { barycentric_to_world(v, f, bary, n, world); }
+}
+#elif defined(REF_SR)
+#include "stratifiedTransientRenderer.h"
+#include "stratifiedStreamedTransientRenderer.h"
+#include "stratifiedStreamedGradientRenderer.h"
+extern "C" {
+void ref_sr_render_transient(float* o, float* n, float* v, int V, int* f, int F, int S, float lb, float ub, float res, double* T, double* pl) {
+    render_transient(o, n, v, V, f, F, S, lb, ub, res, T, pl); }
+void ref_sr_streamed_render_transient(float* o, int L, float* n, float* v, int V, float* vn, float* va, int* f, int F, int S, float lb, float ub, float res, double* T, double* pl) {
+    streamed_render_transient(o, L, n, v, V, vn, va, f, F, S, lb, ub, res, T, pl); }
+void ref_sr_streamed_render_gradient(double* data, float* o, int L, float* n, float* v, int V, int* f, int F, int S, float lb, float ub, float res, int w, double* T, double* pl, double* g) {
+    streamed_render_gradient(data, o, L, n, v, V, f, F, S, lb, ub, res, w, T, pl, g); }
+void ref_sr_streamed_render_curvature_grad(float* v, int V, int* f, int F, double* g) { streamed_render_curvature_grad(v, V, f, F, g); }
 }
 #else
 #include "stratifiedStreamedTransientRenderer.h"

@@ -21,7 +21,7 @@ REFERENCE_ROOT = '/root/reference/transient_rendering_cython'
 
 
 def available():
-    return all(os.path.exists(os.path.join(_REF, 'libref_%s.so' % m)) for m in ('renderer', 'ggx', 'jitter', 'intersector'))
+    return all(os.path.exists(os.path.join(_REF, 'libref_%s.so' % m)) for m in ('renderer', 'ggx', 'jitter', 'intersector', 'sr'))
 
 
 def build():
@@ -204,3 +204,32 @@ def set_threads(n):
     intensity[triangle] from every worker without synchronisation (smoothed_transient/transient_and_gradient.cpp:116, ggx/...:121): a data
     race under TBB and under the stand-in alike, so intensity is pinned with one thread."""
     C.CDLL('libgomp.so.1').omp_set_num_threads(int(n))
+
+
+# ---- first-generation renderer (stratified_transient_raytracer/)
+def sr_transient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, vertex_normal=None, vertex_albedo=None):
+    o, n, v, f = _scene(np.reshape(origin, (-1, 3)), np.reshape(normal, (-1, 3)), vertices, faces); vn, va = _f(vertex_normal), _f(vertex_albedo)
+    L, B = o.shape[0], _bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B)
+    _lib('sr').ref_sr_streamed_render_transient(_pf(o), L, _pf(n), _pf(v), v.shape[0], _pf(vn), _pf(va), _pi(f), f.shape[0], int(num_sample), C.c_float(lower),
+                                                C.c_float(upper), C.c_float(resolution), _pd(T), _pd(pl))
+    return T, pl
+
+
+def sr_render_transient(origin, normal, vertices, faces, num_sample, lower, upper, resolution):
+    """single-origin render_transient (stratifiedTransientRenderer.cpp:132-218)."""
+    o = _f(origin).reshape(3); n = _f(normal).reshape(3); v = _f(vertices); f = np.ascontiguousarray(faces, dtype=np.int32)
+    B = _bins(lower, upper, resolution); T = np.zeros(B); pl = np.zeros(B)
+    _lib('sr').ref_sr_render_transient(_pf(o), _pf(n), _pf(v), v.shape[0], _pi(f), f.shape[0], int(num_sample), C.c_float(lower), C.c_float(upper),
+                                       C.c_float(resolution), _pd(T), _pd(pl))
+    return T, pl
+
+
+def sr_gradient(origin, normal, vertices, faces, num_sample, lower, upper, resolution, w_width, data):
+    o, n, v, f = _scene(origin, normal, vertices, faces)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    L, B = o.shape[0], _bins(lower, upper, resolution)
+    T = np.zeros((L, B)); pl = np.zeros(B); G = np.zeros((v.shape[0] + 2, 3))       # +2 rows: the reference writes one double past V*3 (index slip)
+    _lib('sr').ref_sr_streamed_render_gradient(_pd(data), _pf(o), L, _pf(n), _pf(v), v.shape[0], _pi(f), f.shape[0], int(num_sample), C.c_float(lower),
+                                               C.c_float(upper), C.c_float(resolution), int(w_width), _pd(T), _pd(pl), _pd(G))
+    return T, G[:v.shape[0]], pl

@@ -46,6 +46,13 @@ def occluder():
     return scenes.merge([ico(), scenes.quad(0.3, 0.05, 0.02, 0.0)])
 
 
+def backface():
+    """bumpy sphere plus a quad wound AWAY from the wall (visible from behind): separates the unclamped first-generation form factor
+    (contributes ff^2) from the clamped second-generation one (contributes 0)."""
+    qv, qf = scenes.quad(0.4, 0.05, -0.17, 0.1)
+    return scenes.merge([ico(), (qv, np.ascontiguousarray(qf[:, ::-1]))])
+
+
 def albedo(v):
     return (0.5 + np.random.RandomState(0).rand(v.shape[0])).astype(np.float32)
 
@@ -93,8 +100,14 @@ CASES = {
     'jitter_transient_sh':  dict(kind='jitter_transient', scene='ico', S=S, offset=8, shading=True),
     'jitter_gradient_t1':   dict(kind='jitter_gradient', scene='ico', S=S, offset=8, tf=1),
     'jitter_gradient_t0':   dict(kind='jitter_gradient', scene='occluder', S=S, offset=8, tf=0),
+    # first-generation renderer (stratified_transient_raytracer/)
+    'sr_transient_backface': dict(kind='sr_transient', scene='backface', S=S),
+    'sr_transient_albedo':  dict(kind='sr_transient', scene='occluder', S=S, albedo=True),
+    'sr_single_origin':     dict(kind='sr_single', scene='backface', S=4 * S, source=5),
+    'sr_gradient_w0':       dict(kind='sr_gradient', scene='occluder', S=S, w=0),
+    'sr_gradient_w3':       dict(kind='sr_gradient', scene='backface', S=S, w=3),
 }
-SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder}
+SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder, 'backface': backface}
 
 
 def run_case(impl, oracle, c, seed=None, relabel=None):
@@ -139,6 +152,17 @@ def run_case(impl, oracle, c, seed=None, relabel=None):
     if k == 'vertex_gradient':
         G = impl.vertex_gradient(c['vertex'], o[:1], n[:1], v, f_, c['S'], LB, UB, RES_VG, c['rs'], c['sb'], **kw)
         return {'VG': np.asarray(G).reshape(-1, 3)}
+    if k == 'sr_transient':
+        T = impl.sr_transient(o_, n_, v, f_, c['S'], LB, UB, RES, vertex_normal=vn, vertex_albedo=va, **kw)[0]
+        return {'T': T[inv_s]}
+    if k == 'sr_single':
+        i = c['source']
+        return {'T': np.asarray(impl.sr_render_transient(o[i], n[i], v, f_, c['S'], LB, UB, RES, **kw)[0]).reshape(1, -1)}
+    if k == 'sr_gradient':
+        v2 = v.copy(); v2[:, 2] += 0.01
+        data = oracle.sr_transient(o, n, v2, f, c['S'], LB, UB, RES, seed=5)[0]
+        T, G, _ = impl.sr_gradient(o_, n_, v, f_, c['S'], LB, UB, RES, c['w'], data[sp], **kw)
+        return {'T': T[inv_s], 'G': G}
     jw, jg = jitter_kernel()
     if k == 'jitter_transient':
         T = impl.jitter_transient(o_, n_, v, f_, c['S'], LB, UB, RES, jw, c['offset'], vertex_normal=vn, **kw)[0]
@@ -157,6 +181,17 @@ class OracleAdapter(object):
         self.o = oracle
         for name in ('transient', 'intensity', 'gradient', 'vertex_gradient', 'jitter_transient', 'jitter_gradient'):
             setattr(self, name, getattr(oracle, name))
+
+    # first generation: the reference's gradient is pinned with its output-index slips reproduced (typos=True; see render_gradients_sr)
+    def sr_transient(self, *a, **kw):
+        return self.o.sr_transient(*a, **kw)
+
+    def sr_render_transient(self, o, n, v, f, S, lb, ub, res, seed=None):
+        T, pl = self.o.sr_transient(np.reshape(o, (1, 3)), np.reshape(n, (1, 3)), v, f, S, lb, ub, res, **({} if seed is None else {'seed': seed}))
+        return T[0], pl
+
+    def sr_gradient(self, o, n, v, f, S, lb, ub, res, w, data, seed=None):
+        return self.o.sr_gradient(o, n, v, f, S, lb, ub, res, w, data, typos=True, **({} if seed is None else {'seed': seed}))
 
     def gradient_albedo(self, o, n, v, f, S, lb, ub, res, data, w, rs, sb, va, seed=None):
         return self.o.gradient(o, n, v, f, S, lb, ub, res, data, w, rs, sb, 1, 0, vertex_albedo=va, kind=1, **({} if seed is None else {'seed': seed}))

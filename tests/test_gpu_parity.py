@@ -380,6 +380,44 @@ def test_jitter_temporal_kernel(oracle, gpu_ctx):
         assert np.linalg.norm(G_ref) > 0 and rel_l2(G, G_ref) <= TOL_GRADIENT
 
 
+def test_first_generation_api(oracle, gpu_ctx):
+    """stratified_transient_raytracer/ module (`renderer_sr`): unclamped forward, single-origin renderTransient,
+    gradient with the twice-applied box filter, one tap, normal-variation term always on, '=' into the gradient."""
+    from nlos_surface_optimization_b200 import renderer_sr, scenes
+    qv, qf = scenes.quad(0.4, 0.05, -0.17, 0.1)
+    v, f = scenes.merge([scenes.icosphere(3, 0.1, (0.02, -0.03, 0.45), noise=0.03, seed=3), (qv, np.ascontiguousarray(qf[:, ::-1])),
+                         scenes.quad(0.3, 0.04, 0.03, 0.0)])
+    o, n = scenes.wall_grid(5); ns = 6 * f.shape[0]
+    T_ref, pl_ref = oracle.sr_transient(o, n, v, f, ns, LB, UB, RES)
+    T_st = oracle.transient(o, n, v, f, ns, LB, UB, RES)[0]
+    assert T_ref.sum() > 1.0005 * T_st.sum()                       # the back-facing quad only shows without the clamp
+    B = T_ref.shape[1]
+    T = np.full((o.shape[0], B), 3.0); pl = np.zeros(B)
+    renderer_sr.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, T, pl, ctx=gpu_ctx)
+    assert np.array_equal(pl, pl_ref) and rel_l2(T, T_ref) <= TOL_TRANSIENT
+    vn = scenes.vertex_normals(v, f); va = (0.5 + np.random.RandomState(2).rand(v.shape[0])).astype(np.float32)
+    renderer_sr.renderStreamedTransientShading(o, n, v, vn, f, ns, LB, UB, RES, T, pl, ctx=gpu_ctx)
+    assert rel_l2(T, oracle.sr_transient(o, n, v, f, ns, LB, UB, RES, vertex_normal=vn)[0]) <= TOL_TRANSIENT
+    renderer_sr.renderStreamedTransientwAlbedo(o, n, v, va, f, ns, LB, UB, RES, T, pl, ctx=gpu_ctx)
+    assert rel_l2(T, oracle.sr_transient(o, n, v, f, ns, LB, UB, RES, vertex_albedo=va)[0]) <= TOL_TRANSIENT
+    # single origin
+    t1 = np.zeros(B); renderer_sr.renderTransient(o[7], n[7], v, f, ns, LB, UB, RES, t1, pl, ctx=gpu_ctx)
+    assert rel_l2(t1, oracle.sr_transient(o[7:8], n[7:8], v, f, ns, LB, UB, RES)[0][0]) <= TOL_TRANSIENT
+    # gradient
+    v2 = v.copy(); v2[:, 2] += 0.01
+    data = oracle.sr_transient(o, n, v2, f, ns, LB, UB, RES)[0]
+    for w in (0, 2, 7):
+        T_ref, G_ref, _ = oracle.sr_gradient(o, n, v, f, ns, LB, UB, RES, w, data)
+        T = np.zeros((o.shape[0], B)); G = np.full((v.shape[0], 3), 5.0)      # '=' semantics: the 5s must disappear
+        renderer_sr.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, w, T, pl, G, data, ctx=gpu_ctx)
+        assert rel_l2(T, T_ref) <= TOL_TRANSIENT
+        assert np.linalg.norm(G_ref) > 0 and rel_l2(G, G_ref) <= TOL_GRADIENT, (w, rel_l2(G, G_ref))
+    # a second-generation call afterwards is unaffected by the first-generation mode
+    from nlos_surface_optimization_b200 import renderer
+    renderer.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, T, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(T, T_st) <= TOL_TRANSIENT
+
+
 def test_sharded_rendering_nccl_two_gpus(oracle, tmp_path):
     """dist.inverse_rendering_sharded over NCCL on 2 GPUs (skipped on a 1-GPU box): all-reduced gradient and gathered
     transient equal the single-GPU call."""
