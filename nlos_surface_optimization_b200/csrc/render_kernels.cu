@@ -66,10 +66,10 @@ __device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGe
 constexpr int kQCap = 64;        // ray queue capacity per warp (power of two, >= 63)
 constexpr int kTile = 256;       // sample slots per warp pass == visibility words in the warp tile
 #ifndef NLOS_REFILL
-#define NLOS_REFILL 16
+#define NLOS_REFILL 24
 #endif
 #ifndef NLOS_MINLANES
-#define NLOS_MINLANES 8
+#define NLOS_MINLANES 6
 #endif
 #ifndef NLOS_FWD_MINBLOCKS
 #define NLOS_FWD_MINBLOCKS 4

@@ -25,4 +25,15 @@ renderer.renderStreamedNormalSmoothing(v, f, scenes.face_affinity(f), G, ctx=ctx
 ctx.set_option('reuse_visibility', 0)
 renderer.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, T, pl, G, data, w, 10, 1, 1, 0, ctx=ctx)
 vis, cnt = nb.debug_visibility(o, v, f, ns, ctx=ctx)
+ctx.set_option('reuse_visibility', 1)
+from nlos_surface_optimization_b200 import jitter, embree_intersector, renderer_sr
+jw = np.ascontiguousarray((np.exp(-0.5 * ((np.arange(9) - 3) / 2.0) ** 2) / 5).reshape(-1, 1)); jg = np.ascontiguousarray(np.gradient(jw[:, 0]).reshape(-1, 1))
+jitter.renderStreamedTransient(o, n, v, f, ns, lb, ub, res, T, pl, jw, 3, ctx=ctx)
+jitter.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, jw, jg, 3, T, pl, G, data, w, 1, ctx=ctx)
+renderer_sr.renderStreamedTransient(o, n, v, f, ns, lb, ub, res, T, pl, ctx=ctx)
+t1 = np.zeros(B); renderer_sr.renderTransient(o[0], n[0], v, f, ns, lb, ub, res, t1, pl, ctx=ctx)
+renderer_sr.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, 3, T, pl, G, data, ctx=ctx)
+ro = np.tile(o, (8, 1)).astype(np.float32); rd = np.tile(np.array([[0.02, -0.04, 1.0]], np.float32), (ro.shape[0], 1))
+bc = np.zeros((ro.shape[0], 3), np.float32); embree_intersector.embree3_tbb_intersection(ro, rd, v, f, bc)
+pw = np.zeros((ro.shape[0], 3), np.float32); embree_intersector.barycoord_to_world(v, f, bc, pw)
 print('sanitize run ok', T.sum(), np.abs(G).sum(), vis.mean())
