@@ -95,16 +95,9 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
   if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += blockDim.x) s_w[i] = wprefix[i]; __syncthreads(); }
   const int lane = threadIdx.x & 31;
   WarpShared& ws = ws_all[threadIdx.x >> 5];
-#ifndef NLOS_SPLIT_TILES  // all warps of a block share ONE triangle tile and split the slot chunks among them: they walk the same
-                          // BVH region at the same time, which keeps it in L1 (measured 26.8 vs 31.4 ms with one tile per warp)
-#ifdef NLOS_SWAP_GRID
-  const int p = blockIdx.y * 32 + lane;
-#else
+  // all warps of a block share ONE triangle tile and split the slot chunks among them: they walk the same BVH region at the
+  // same time, which keeps it in L1 (measured 26.8 vs 31.4 ms with one tile per warp)
   const int p = blockIdx.x * 32 + lane;
-#endif
-#else
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-#endif
   const bool active = p < sc.F;
   const int warp_global = p >> 5;
   TriRegs t;
@@ -115,15 +108,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
   const int64_t total_slots = P.L * (int64_t)P.spp;
   const int64_t nchunks = (total_slots + P.chunk - 1) / P.chunk;
   const unsigned lt = (1u << lane) - 1u;
-#ifndef NLOS_SPLIT_TILES
-#ifdef NLOS_SWAP_GRID
-  for (int64_t chunk = (int64_t)blockIdx.x * (kFwdBlock / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += (int64_t)gridDim.x * (kFwdBlock / 32)) {
-#else
   for (int64_t chunk = (int64_t)blockIdx.y * (kFwdBlock / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += (int64_t)gridDim.y * (kFwdBlock / 32)) {
-#endif
-#else
-  for (int64_t chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
-#endif
     const int64_t slot0 = chunk * P.chunk;
     const int nslots = (int)(total_slots - slot0 < P.chunk ? total_slots - slot0 : P.chunk);
     if (WRITE_VIS) { for (int i = lane; i < nslots; i += 32) ws.tile[i] = 0u; }
@@ -131,12 +116,6 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
     int gen = 0, qhead = 0, qcount = 0;
     // per-lane traversal state of the ray in flight (cur == kSentinel: lane is idle)
     int cur = kSentinel, sp = 0, stack[kStack];
-#ifdef NLOS_TOPCACHE
-    int top = kDone;      // top of the traversal stack lives in a register: a pop uses it at once and the refill load is off the critical path
-#endif
-#if defined(NLOS_EXPERIMENT_EXTRALOAD) || defined(NLOS_EXPERIMENT_EXTRAALU)
-    float sink = 0.f;
-#endif
     Ray ray; float ts = 0.f, val = 0.f; int bin = -1, prim = 0, tri_lane = 0, slot_local = 0; int64_t src = 0;
     ray.o = ray.d = ray.id = ray.oid = mk3(0.f, 0.f, 0.f);
     for (;;) {
@@ -204,9 +183,6 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
           src = P.spp == 1 ? slot : slot / P.spp;
           ray = make_ray(xyz(__ldg(P.origin + src)), mk3(ws.dx[pos], ws.dy[pos], ws.dz[pos]));
           stack[0] = kDone; sp = 1; cur = sc.root_count > 0 ? leaf_ref(0, sc.root_count) : 0;
-#ifdef NLOS_TOPCACHE
-          top = kDone;
-#endif
         }
         const int prim_new = __shfl_sync(0xffffffffu, t.prim, (meta >> 16) & 31);
         if (fetch) prim = prim_new;
@@ -221,34 +197,12 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         float4 a, b, c, dq;
         ld256(&sc.nodes[cur].a, a, b);
         ld256(&sc.nodes[cur].c, c, dq);
-#ifdef NLOS_EXPERIMENT_EXTRALOAD     // timing experiment only: one redundant 32-byte node fetch per step (same line) to probe L1-boundness
-        { float e0, e1, e2, e3, e4, e5, e6, e7;
-          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(e0), "=f"(e1), "=f"(e2), "=f"(e3), "=f"(e4), "=f"(e5), "=f"(e6), "=f"(e7) : "l"(&sc.nodes[cur].a)); sink += e0 + e4; }
-#endif
-#ifdef NLOS_EXPERIMENT_EXTRAALU      // timing experiment only: 12 redundant min/max per step to probe ALU/issue-boundness
-        { float z = a.x;
-#pragma unroll
-          for (int q = 0; q < 12; ++q) asm volatile("min.f32 %0, %0, %1;" : "+f"(z) : "f"(b.x + (float)q)); sink += z; }
-#endif
         const int r0 = __float_as_int(dq.x), r1 = __float_as_int(dq.y);
         float t0, t1;
         const bool h0 = slab(ray, a.x, a.y, a.z, a.w, b.x, b.y, tlim, t0);
         const bool h1 = slab(ray, b.z, b.w, c.x, c.y, c.z, c.w, tlim, t1);
-#if defined(NLOS_TOPCACHE)
-        {
-          const bool both = h0 && h1, any = h0 || h1, first0 = t0 <= t1;
-          const int nearr = (h0 && (!h1 || first0)) ? r0 : r1;
-          if (both) stack[sp] = top;
-          sp += both ? 1 : 0;
-          const int far = first0 ? r1 : r0;
-          cur = any ? nearr : top;
-          int below = top;
-          if (!any) below = stack[sp - 1];
-          sp -= any ? 0 : 1;
-          top = both ? far : below;
-        }
-#elif !defined(NLOS_BRANCHY)      // fully predicated child selection: no BSSY/BSYNC pair inside the step (measured 33.3 vs 35.8 ms)
-        {
+        {   // fully predicated child selection: no BSSY/BSYNC pair inside the step (measured 33.3 vs 35.8 ms with if/else).
+            // Keeping the stack top in a register (pop without a dependent local load) was measured SLOWER (27.8 vs 26.8 ms).
           const bool both = h0 && h1, any = h0 || h1, first0 = t0 <= t1;
           const int nearr = (h0 && (!h1 || first0)) ? r0 : r1;
           if (both) stack[sp] = first0 ? r1 : r0;
@@ -258,12 +212,6 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
           sp -= any ? 0 : 1;
           cur = any ? nearr : popped;
         }
-#else
-        if (h0 && h1) { const bool first0 = t0 <= t1; stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1; }
-        else if (h0) cur = r0;
-        else if (h1) cur = r1;
-        else cur = stack[--sp];
-#endif
 #if NLOS_MINLANES > 0
         if (__popc(__activemask()) < NLOS_MINLANES) break;
 #endif
@@ -272,11 +220,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         const int first = leaf_first(cur), cnt = leaf_count(cur);
         bool occ = false;
         for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes_fast(sc.ttris, first + j, ray, ts, prim);
-#ifdef NLOS_TOPCACHE
-        cur = occ ? kSentinel : top; top = stack[--sp];
-#else
         cur = occ ? kSentinel : stack[--sp];                     // occluded: drop the ray
-#endif
       }
       if (cur == kDone) {                                        // traversal finished without an occluder: visible
         const double dv = (double)val / (double)P.spp;           // TG.cpp:231-232
@@ -299,9 +243,6 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         cur = kSentinel;
       }
     }
-#if defined(NLOS_EXPERIMENT_EXTRALOAD) || defined(NLOS_EXPERIMENT_EXTRAALU)
-    if (sink == 1234.5678f) out[0] = sink;
-#endif
     if (WRITE_VIS) {
       __syncwarp();
       if (warp_global * 32 < sc.F) for (int i = lane; i < nslots; i += 32) vis[(size_t)(slot0 + i) * P.words_per_row + warp_global] = ws.tile[i];
@@ -540,15 +481,7 @@ inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
-#ifndef NLOS_SPLIT_TILES
-#ifdef NLOS_SWAP_GRID
-  const dim3 grid((unsigned)std::min<int64_t>((nchunks + kFwdBlock / 32 - 1) / (kFwdBlock / 32), 1 << 20), (unsigned)((sc.F + 31) / 32), 1);
-#else
   const dim3 grid((unsigned)((sc.F + 31) / 32), (unsigned)std::min<int64_t>((nchunks + kFwdBlock / 32 - 1) / (kFwdBlock / 32), 65535), 1);
-#endif
-#else
-  const dim3 grid((unsigned)((sc.F + kFwdBlock - 1) / kFwdBlock), (unsigned)std::min<int64_t>(nchunks, 65535), 1);
-#endif
   const size_t smem = (kFwdBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
   if (smem > 48 * 1024) {      // long tap tables (large refine_scale * sigma_bin) need the opt-in shared-memory limit
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -47,6 +47,42 @@ struct SahBuilder {
   }
 };
 
+// ---- packet experiment: rays of one (32-triangle tile, 64-source chunk) are compacted in slot order (as k_forward's phase A does)
+// and traversed 32 at a time with ONE shared stack: a node is entered when any live lane's ray hits its box.  Counts what a
+// warp-packet kernel would execute, to compare with the per-lane traversal (lane-slots = node visits x 32 lanes).
+static int g_packet = 0;          // 0: off, 1: row-major chunks of 64 sources, 2: 8x8 wall tiles (wall is WxW)
+static int g_wall = 64;
+extern "C" void bvh_quality_packet(int mode, int wall) { g_packet = mode; g_wall = wall; }
+struct PRay { Ray ray; float ts; int prim; };
+static void packet_trace(const std::vector<BvhNode>& nodes, const std::vector<float4>& ttris, const PRay* pr, int n,
+                         unsigned long long& visits, unsigned long long& lane_box, unsigned long long& leaf_visits, unsigned long long& lane_tri,
+                         unsigned long long& useful_box) {
+  bool alive[32]; int nalive = n; for (int i = 0; i < n; ++i) alive[i] = true;
+  int stack[256]; int sp = 0; int cur = 0;
+  auto leaf = [&](int ref, const bool* hit) {
+    ++leaf_visits; const int f0 = leaf_first(ref), c0 = leaf_count(ref);
+    for (int i = 0; i < n; ++i) if (alive[i] && hit[i]) { lane_tri += c0;
+      for (int j = 0; j < c0; ++j) if (tri_occludes(ttris.data(), f0 + j, pr[i].ray, pr[i].ts, pr[i].prim)) { alive[i] = false; --nalive; break; } }
+  };
+  while (nalive > 0) {
+    const BvhNode& nd = nodes[cur]; ++visits; lane_box += 32;
+    bool h0[32], h1[32]; bool any0 = false, any1 = false; float t0f = 0, t1f = 0; bool have = false;
+    for (int i = 0; i < n; ++i) { h0[i] = h1[i] = false; if (!alive[i]) continue; const float tlim = pr[i].ts * 1.000001f; float t0, t1;
+      h0[i] = slab(pr[i].ray, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, tlim, t0);
+      h1[i] = slab(pr[i].ray, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, tlim, t1);
+      if (h0[i] || h1[i]) ++useful_box;
+      if (!have && (h0[i] || h1[i])) { have = true; t0f = h0[i] ? t0 : 3e38f; t1f = h1[i] ? t1 : 3e38f; }
+      any0 |= h0[i]; any1 |= h1[i]; }
+    int r0 = nd.d.x, r1 = nd.d.y;
+    if (any0 && r0 < 0) { leaf(r0, h0); any0 = false; }
+    if (any1 && r1 < 0) { leaf(r1, h1); any1 = false; }
+    if (nalive == 0) break;
+    if (any0 && any1) { const bool first0 = t0f <= t1f; stack[sp++] = first0 ? r1 : r0; cur = first0 ? r0 : r1; }
+    else if (any0) cur = r0; else if (any1) cur = r1;
+    else { if (sp == 0) break; cur = stack[--sp]; }
+  }
+}
+
 extern "C" {
 // mode 0: LBVH (Karras, leaf runs <= leafmax) ; mode 1: binned SAH.  Returns per-ray averages in out[0..3] = {rays, box/ray, tri/ray, nodes}
 int bvh_quality(const float* origin, int L, const float* verts, int V, const int* faces, int F, int mode, int leafmax, float padscale, double* out, int* hist /*64 bins of node visits per ray*/) {
@@ -79,6 +115,28 @@ int bvh_quality(const float* origin, int L, const float* verts, int V, const int
     f3 N=cross3(v2-v1,v3-v1); float A=len3(N)/2; f3 nf=N/(2*A); stris[4*p]=make_float4(v1.x,v1.y,v1.z,A); stris[4*p+1]=make_float4(v2.x,v2.y,v2.z,nf.x); stris[4*p+2]=make_float4(v3.x,v3.y,v3.z,nf.y); stris[4*p+3]=make_float4(nf.z,0,0,0);}
   // leafmax>4 cannot be encoded by child_ref (2 bits) -> only occluded() (count field) is used here
   unsigned long long nb=0, nt=0, nr=0; for (int i=0;i<64;++i) hist[i]=0;
+  if (g_packet && root_count == 0) {
+    unsigned long long visits = 0, lane_box = 0, leaf_visits = 0, lane_tri = 0, useful = 0, npk = 0, ind_box = 0, ind_tri = 0;
+    const int W = g_wall; const int nchunk = L / 64;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      int src[64];
+      for (int q = 0; q < 64; ++q) { if (g_packet == 1) src[q] = ch * 64 + q; else { const int tx = ch % (W / 8), ty = ch / (W / 8); src[q] = (ty * 8 + q / 8) * W + tx * 8 + q % 8; } }
+      for (int p0 = 0; p0 < F; p0 += 32) {
+        std::vector<PRay> q;
+        for (int qi = 0; qi < 64; ++qi) { const int s = src[qi]; if (s >= L) continue; f3 o = ldv(origin, s);
+          for (int p = p0; p < std::min(F, p0 + 32); ++p) { ShadeTri st; TriRec tr; st.v1=xyz(stris[4*p]);st.A=stris[4*p].w;st.v2=xyz(stris[4*p+1]);st.v3=xyz(stris[4*p+2]);st.nf=mk3(stris[4*p+1].w,stris[4*p+2].w,stris[4*p+3].x);
+            tr.v0=xyz(ttris[4*p]);tr.e1=xyz(ttris[4*p+1]);tr.e2=xyz(ttris[4*p+2]);tr.Ng=xyz(ttris[4*p+3]); int prim=f2i(ttris[4*p].w);
+            SampleGeom g; if(!sample_self_hit(5489,s,prim,0,o,st,tr,g)) continue;
+            float ff=-dot3(st.nf,g.d)*g.d.z; if(!(ff>0)) continue;
+            PRay r; r.ray = make_ray(o, g.d); r.ts = g.t; r.prim = prim; q.push_back(r);
+            uint32_t cb=0,ct=0; occluded(nodes.data(),ttris.data(),root_count,r.ray,g.t,prim,&cb,&ct); ind_box+=cb; ind_tri+=ct; } }
+        for (size_t k = 0; k < q.size(); k += 32) { const int n = (int)std::min<size_t>(32, q.size() - k); packet_trace(nodes, ttris, q.data() + k, n, visits, lane_box, leaf_visits, lane_tri, useful); ++npk; nr += n; }
+      }
+    }
+    out[0]=(double)nr; out[1]=(double)visits/npk; out[2]=(double)leaf_visits/npk; out[3]=(double)nr/npk;
+    out[4]=(double)ind_box/2/nr; out[5]=(double)ind_tri/nr; out[6]=(double)useful/(double)(visits?visits:1); out[7]=(double)lane_tri/nr;
+    return 0;
+  }
   for (int s=0;s<L;++s){ f3 o=ldv(origin,s);
     for (int p=0;p<F;++p){ ShadeTri st; TriRec tr; st.v1=xyz(stris[4*p]);st.A=stris[4*p].w;st.v2=xyz(stris[4*p+1]);st.v3=xyz(stris[4*p+2]);st.nf=mk3(stris[4*p+1].w,stris[4*p+2].w,stris[4*p+3].x);
       tr.v0=xyz(ttris[4*p]);tr.e1=xyz(ttris[4*p+1]);tr.e2=xyz(ttris[4*p+2]);tr.Ng=xyz(ttris[4*p+3]); int prim=f2i(ttris[4*p].w);
