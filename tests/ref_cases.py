@@ -100,6 +100,9 @@ CASES = {
     'jitter_transient_sh':  dict(kind='jitter_transient', scene='ico', S=S, offset=8, shading=True),
     'jitter_gradient_t1':   dict(kind='jitter_gradient', scene='ico', S=S, offset=8, tf=1),
     'jitter_gradient_t0':   dict(kind='jitter_gradient', scene='occluder', S=S, offset=8, tf=0),
+    # the headline mesh (69 630 triangles, real self-occlusion), 2 samples per triangle and source
+    'bunny_transient':      dict(kind='transient', scene='bunny', S=2 * 69630, rs=10, sb=1),
+    'bunny_gradient':       dict(kind='gradient', scene='bunny', S=2 * 69630, rs=10, sb=1, tf=1, lf=0),
     # first-generation renderer (stratified_transient_raytracer/)
     'sr_transient_backface': dict(kind='sr_transient', scene='backface', S=S),
     'sr_transient_albedo':  dict(kind='sr_transient', scene='occluder', S=S, albedo=True),
@@ -107,7 +110,7 @@ CASES = {
     'sr_gradient_w0':       dict(kind='sr_gradient', scene='occluder', S=S, w=0),
     'sr_gradient_w3':       dict(kind='sr_gradient', scene='backface', S=S, w=3),
 }
-SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder, 'backface': backface}
+SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder, 'backface': backface, 'bunny': scenes.bunny}
 
 
 def run_case(impl, oracle, c, seed=None, relabel=None):
@@ -203,10 +206,11 @@ class OracleAdapter(object):
 def two_sample_z(mean_a, std_a, n_a, mean_b, std_b, n_b):
     """Two-sample z per element with the pooled standard deviation (both sides are the same estimator with the same sample count, so
     their per-element variances are equal; pooling keeps z well behaved when one side has few draws).  Elements without spread on
-    either side are skipped.  Returns (z, relative L2 distance of the means)."""
+    either side are skipped.  Returns (z, relative L2 distance of the means, the same distance expected from noise alone)."""
     pooled = np.sqrt(((n_a - 1) * std_a ** 2 + (n_b - 1) * std_b ** 2) / (n_a + n_b - 2))
     se = pooled * np.sqrt(1.0 / n_a + 1.0 / n_b)
     ok = se > 0
     z = (mean_a[ok] - mean_b[ok]) / se[ok]
     rel = np.linalg.norm(mean_a - mean_b) / max(np.linalg.norm(mean_b), 1e-300)
-    return z, rel
+    noise_rel = np.sqrt((se ** 2).sum()) / max(np.linalg.norm(mean_b), 1e-300)      # what pure Monte-Carlo noise makes of `rel`
+    return z, rel, noise_rel

@@ -8,7 +8,8 @@ this side); what that resolves is printed as `rel` (the relative L2 distance of 
 points (regularisers, ray queries) are compared directly.
 
 Acceptance (stated here, used below), over the n elements with spread:  rms(z) <= 1.30 + 2.5/sqrt(n),  |mean(z)| <= 0.20 + 2/sqrt(n),
-max|z| <= 10, and the two means within 3 % in L2 (cases with fewer than 4 numbers: |z| <= 4.5).  z is t-like (R + K - 2 degrees of
+max|z| <= 10, and the two means within 3 % in L2 or within 1.5x the distance Monte-Carlo noise alone produces (cases with fewer than
+4 numbers: |z| <= 4.5).  z is t-like (R + K - 2 degrees of
 freedom: rms ~ 1.1, heavy tails) and neighbouring bins are correlated by the smoothing, hence the n-dependent slack; a systematic
 error of one standard error (a few 1e-3 of the signal) in every element would move mean(z) to 1.
 K (draws on this side): the oracle's literal gradient loop costs seconds per draw, so the CPU tests use 3 draws for gradient-type
@@ -40,9 +41,9 @@ def fixture():
 
 def check(name, key, mean_r, std_r, R, draws):
     d = np.stack(draws)
-    z, rel = rc.two_sample_z(d.mean(0), d.std(0, ddof=1), d.shape[0], mean_r, std_r, R)
+    z, rel, noise_rel = rc.two_sample_z(d.mean(0), d.std(0, ddof=1), d.shape[0], mean_r, std_r, R)
     assert z.size > 0, (name, key)
-    msg = '%s/%s n=%d rms z %.3f mean z %+.3f max|z| %.2f rel %.4f' % (name, key, z.size, np.sqrt((z ** 2).mean()), z.mean(), np.abs(z).max(), rel)
+    msg = '%s/%s n=%d rms z %.3f mean z %+.3f max|z| %.2f rel %.4f (noise %.4f)' % (name, key, z.size, np.sqrt((z ** 2).mean()), z.mean(), np.abs(z).max(), rel, noise_rel)
     print(msg)
     if z.size < 4:
         assert np.abs(z).max() <= 4.5, msg
@@ -50,7 +51,7 @@ def check(name, key, mean_r, std_r, R, draws):
     assert np.sqrt((z ** 2).mean()) <= 1.30 + 2.5 / np.sqrt(z.size), msg
     assert abs(z.mean()) <= 0.20 + 2.0 / np.sqrt(z.size), msg
     assert np.abs(z).max() <= 10.0, msg
-    assert rel <= 0.03 or key == 'VG', msg          # VG: one source, 1250 samples per triangle -> noisy means, z still applies
+    assert rel <= max(0.03, 1.5 * noise_rel), msg    # the means agree to 3 %, or to what the Monte-Carlo noise of the case allows
 
 
 @pytest.mark.parametrize('name', sorted(rc.CASES))
