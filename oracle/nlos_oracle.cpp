@@ -4,19 +4,20 @@
 // cpu_baseline / --impl reference legs may load this library.  The product (libnlos_b200.so) never
 // links, imports or calls anything in oracle/.
 //
-// *** PARITY: PINNED STATISTICALLY TO THE REFERENCE'S OWN CODE (not bit-pinned). ***  This is a restatement of the
-// reference's algorithm, written from SURVEY.md Appendix A and the reference sources cited below.  The reference
-// ships no golden vectors and cannot be built as it stands in this image (it needs Embree 3 incl. its
-// tutorial/common headers, Intel MKL VSL, TBB and Boost.Random - none present).  `make -C oracle ref` therefore
-// compiles the reference's UNMODIFIED translation units, where they lie under /root/reference, against the
-// from-scratch stand-in headers of oracle/ref_shim/ into oracle/_ref/ (closest-hit query, parallel_for, 1-D
-// convolution and mt19937 are the stand-ins; every line of rendering/gradient arithmetic is the reference's).
-// tools/make_ref_fixtures.py runs them into tests/golden/ref_pin.npz and tests/test_reference_pin.py checks this
-// oracle (and the CUDA path) against those outputs: two-sample z tests for the Monte-Carlo entry points (the
-// reference's Mersenne-Twister streams are unrelated to the counter-based generator used here, so agreement is
-// to a few 1e-3 of the signal, not to the bit), direct comparison for the regularisers and the ray queries.
-// Bit-level behaviour is pinned against mathematics instead: closed-form cases, brute-force-vs-BVH agreement and
-// term-by-term finite differences (tests/test_oracle.py).
+// *** PARITY: PINNED TO THE REFERENCE'S OWN CODE. ***  This is a restatement of the reference's algorithm, written from
+// SURVEY.md Appendix A and the reference sources cited below.  The reference ships no golden vectors and cannot be built
+// as it stands in this image (it needs Embree 3 incl. its tutorial/common headers, Intel MKL VSL, TBB and Boost.Random -
+// none present).  `make -C oracle ref` therefore compiles the reference's UNMODIFIED translation units, where they lie
+// under /root/reference, against the from-scratch stand-in headers of oracle/ref_shim/ into oracle/_ref/ (closest-hit
+// query, parallel_for, 1-D convolution and mt19937 are the stand-ins; every line of sampling, rendering and gradient
+// arithmetic is the reference's).  tools/make_ref_fixtures.py runs them into tests/golden/ref_pin.npz and
+// tests/test_reference_pin.py checks this oracle against those outputs
+//   (1) on the reference's own sample stream (test hook nlos_oracle_set_external_samples): every entry point reproduces the
+//       reference's numbers to float rounding (1e-7 ... 1e-4; the reference is plain -O2 code, so not to the bit);
+//   (2) with its own counter-based generator: two-sample z tests at 4e5 samples per source;
+//   (3) regularisers and ray queries directly.
+// Bit-level behaviour (what the CUDA path must match exactly) is pinned against mathematics: closed-form cases,
+// brute-force-vs-BVH agreement and term-by-term finite differences (tests/test_oracle.py).
 //
 // What is restated (file:line relative to /root/reference/transient_rendering_cython/):
 //   forward task          smoothed_transient/transient_and_gradient.cpp:122-237   (GGX: ggx/transient_and_gradient.cpp:126-243)
@@ -101,6 +102,17 @@ static inline void sample_ST(uint64_t seed, int64_t src, int tri, int k, float& 
   philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)tri, (uint32_t)src, (uint32_t)(k >> 1), (uint32_t)((uint64_t)src >> 32), o);
   if (k & 1) { S = bits_to_unit(o[2]); T = bits_to_unit(o[3]); } else { S = bits_to_unit(o[0]); T = bits_to_unit(o[1]); }
 }
+
+// Test hook: an EXTERNAL sample stream replaces the counter-based generator, so that the oracle can be run on exactly the samples
+// the reference's own code drew (its single-threaded Mersenne-Twister stream; tests/test_reference_pin.py "same-sample" cases).
+// Layout = the order the reference consumes its stream with one worker: task (source, triangle) in index order, spp pairs (S, T).
+static const float* g_ext_samples = nullptr; static int64_t g_ext_count = 0;
+// Two places where the reference does not consume its stream in plain task order (only relevant while a stream is installed):
+//  * the per-bin vertex gradient returns BEFORE drawing for triangles that do not touch the vertex (TG.cpp:725-727), so the n-th
+//    adjacent task reads the n-th block of the stream                                     -> g_ext_task (>= 0 overrides the task index)
+//  * the first-generation gradient call keeps ONE sampler set for its forward and its gradient pass (SR/SSG.cpp:400-470), so the
+//    gradient pass continues where the forward pass stopped                               -> g_ext_base (floats to skip)
+static int64_t g_ext_task = -1, g_ext_base = 0;
 
 // ---------------------------------------------------------------- triangle in Embree's TriangleM form
 struct TriRec { V3 v0, e1, e2, Ng; };   // e1=v0-v1, e2=v2-v0, Ng=cross(e2,e1)
@@ -331,7 +343,13 @@ static inline TriSetup setup_tri(const Params& p, int f) {
 struct Sample { bool visible; bool in_range; float u, v, w, r; V3 d; };
 static inline Sample trace_sample(const Scene& sc, const Params& p, const TriSetup& ts, int f, int64_t s_local, int k, TraceStats* st) {
   Sample sm; sm.visible = false; sm.in_range = false;
-  float S, T; sample_ST(p.seed, p.src_offset + s_local, f, k, S, T);
+  float S, T;
+  if (g_ext_samples) {
+    const int64_t task = g_ext_task >= 0 ? g_ext_task : (p.src_offset + s_local) * (int64_t)p.F + f;
+    const int64_t idx = g_ext_base + 2 * (task * spp_of(p) + k);
+    if (idx + 1 >= g_ext_count) return sm;                           // stream exhausted: treated as not visible (tests size it)
+    S = g_ext_samples[idx]; T = g_ext_samples[idx + 1];
+  } else sample_ST(p.seed, p.src_offset + s_local, f, k, S, T);
   float sqrtT = sqrtf(T);
   float u = 1 - sqrtT, v = (1 - S) * sqrtT, w = S * sqrtT;
   V3 o = ld3(p.origin, s_local);
@@ -621,6 +639,7 @@ static void render_vertex_gradient(const Scene& sc, const Params& p, int r, int 
     for (int f = 0; f < p.F; ++f) {
       TriSetup ts = setup_tri(p, f);
       if (ts.i1 != vertex_num && ts.i2 != vertex_num && ts.i3 != vertex_num) continue;
+      if (g_ext_samples) ++g_ext_task;                               // see g_ext_task
       for (int k = 0; k < spp; ++k) {
         Sample sm = trace_sample(sc, p, ts, f, src, k, nullptr);
         if (!sm.visible || !sm.in_range) continue;
@@ -643,6 +662,7 @@ static void render_vertex_gradient(const Scene& sc, const Params& p, int r, int 
       }
     }
   }
+  g_ext_task = -1;
   for (size_t i = 0; i < acc.size(); ++i) gradient[i] += acc[i] / (double)p.L;
 }
 
@@ -710,7 +730,9 @@ int nlos_oracle_sr_gradient(const double* data, const float* origin, int64_t L, 
   fill_pathlengths(p, pathlengths);
   render_transients(sc, p, 1, 1, transient, nullptr, nullptr);
   std::vector<double> diff; sr_difference(p, data, transient, w_width, diff);
+  if (g_ext_samples) g_ext_base = 2 * (int64_t)L * F * spp_of(p);   // see g_ext_base
   render_gradients_sr(sc, p, diff.data(), gradient, typos);
+  g_ext_base = 0;
   return 0;
 }
 
@@ -791,6 +813,8 @@ void nlos_oracle_bary_to_world(const float* verts, const int32_t* faces, const f
 }
 
 // helpers exported for unit tests
+// see g_ext_samples; pass (nullptr, 0) to return to the built-in generator.  The array must stay alive while it is installed.
+void nlos_oracle_set_external_samples(const float* st, int64_t n) { g_ext_samples = st; g_ext_count = n; }
 void nlos_oracle_philox(uint64_t seed, int64_t src, int tri, int k, float* S, float* T) { sample_ST(seed, src, tri, k, *S, *T); }
 int nlos_oracle_isect(const float* v /*9*/, const float* o, const float* d, float* tuv) {
   TriRec tr = make_tri(ld3(v, 0), ld3(v, 1), ld3(v, 2)); float t, u, w;

@@ -1,8 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/nlos_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package never imports this module.  PARITY: pinned statistically to the reference's
-own code (oracle/_ref, tests/test_reference_pin.py), not bit-pinned: see the header of nlos_oracle.cpp.
+--impl reference legs.  The product package never imports this module.  PARITY: pinned to the reference's own code
+(oracle/_ref, tests/test_reference_pin.py: same samples -> same numbers to float rounding): see the header of nlos_oracle.cpp.
 """
 import ctypes as C
 import math
@@ -252,3 +252,17 @@ def sr_gradient(origin, normal, vertices, faces, num_sample, lower, upper, resol
                                   C.c_int(w_width), _p(T, C.c_double), _p(pl, C.c_double), _p(G, C.c_double), C.c_uint64(seed), C.c_int64(src_offset),
                                   C.c_int(1 if brute else 0), C.c_int(1 if typos else 0))
     return T, G, pl
+
+
+_EXT = None
+
+
+def set_external_samples(stream):
+    """Install (or, with None, remove) an external (S,T) sample stream — see g_ext_samples in nlos_oracle.cpp."""
+    global _EXT
+    if stream is None:
+        _EXT = None
+        lib().nlos_oracle_set_external_samples(None, C.c_int64(0))
+        return
+    _EXT = np.ascontiguousarray(stream, dtype=np.float32)
+    lib().nlos_oracle_set_external_samples(_p(_EXT, C.c_float), C.c_int64(_EXT.size))

@@ -25,8 +25,13 @@ void ref_sr_streamed_render_curvature_grad(float* v, int V, int* f, int F, doubl
 #else
 #include "stratifiedStreamedTransientRenderer.h"
 #include "stratifiedStreamedGradientRenderer.h"
+#include <cstddef>
+#include <vector>
+#include "sampler.h"
 extern "C" {
 #if defined(REF_RENDERER)
+// the (S,T) stream a single-threaded reference run consumes: worker 0 of a default-constructed SamplerSet (sampler.cpp:20-33)
+void ref_sampler_stream(int n, float* out) { smp::SamplerSet set(1); for (int i = 0; i < n; ++i) out[i] = set[0](); }
 void ref_streamed_render_intensity(float* o, int L, float* n, float* v, int V, float* vn, int* f, int F, int S, float lb, float ub, double* out) {
     streamed_render_intensity(o, L, n, v, V, vn, f, F, S, lb, ub, out); }
 void ref_streamed_render_transient(float* o, int L, float* n, float* v, int V, float* vn, float* va, int* f, int F, int S, float lb, float ub, float res, double* T, double* pl, int rs, int sb) {

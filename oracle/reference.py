@@ -233,3 +233,10 @@ def sr_gradient(origin, normal, vertices, faces, num_sample, lower, upper, resol
     _lib('sr').ref_sr_streamed_render_gradient(_pd(data), _pf(o), L, _pf(n), _pf(v), v.shape[0], _pi(f), f.shape[0], int(num_sample), C.c_float(lower),
                                                C.c_float(upper), C.c_float(resolution), int(w_width), _pd(T), _pd(pl), _pd(G))
     return T, G[:v.shape[0]], pl
+
+
+def sampler_stream(n):
+    """First n floats of the stream worker 0 draws in every render call (all reference modules share the sampler sources)."""
+    out = np.zeros(int(n), dtype=np.float32)
+    _lib('renderer').ref_sampler_stream(int(n), _pf(out))
+    return out

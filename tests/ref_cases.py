@@ -63,9 +63,11 @@ def jitter_kernel():
     return jw, np.gradient(jw)
 
 
-def target(oracle, v, f, num_sample, res=RES, **kw):
+def target(oracle, v, f, num_sample, res=RES, nsrc=None, **kw):
     """ground-truth transient = the oracle's render of the mesh pushed back by 1 cm (deterministic: fixed seed)."""
     o, n = wall()
+    if nsrc:
+        o, n = o[:nsrc], n[:nsrc]
     v2 = v.copy(); v2[:, 2] += 0.01
     return oracle.transient(o, n, v2, f, num_sample, LB, UB, res, 10, 1, seed=5, **kw)[0]
 
@@ -110,14 +112,53 @@ CASES = {
     'sr_gradient_w0':       dict(kind='sr_gradient', scene='occluder', S=S, w=0),
     'sr_gradient_w3':       dict(kind='sr_gradient', scene='backface', S=S, w=3),
 }
+
+
+def same_sample_cases():
+    """The cases above at a small sample count, to be run by the oracle on the REFERENCE'S OWN sample stream (one reference worker):
+    outputs must then agree to float rounding, not just statistically.  spp = 20 (bunny: 2 sources, spp = 1)."""
+    out = {}
+    for name, c in CASES.items():
+        d = dict(c); F = SCENES[c['scene']]()[1].shape[0]
+        if c['scene'] == 'bunny':
+            d['S'] = F; d['nsrc'] = 2
+        elif c['kind'] == 'vertex_gradient':
+            d['S'] = 50 * F
+        else:
+            d['S'] = 20 * F
+        out[name] = d
+    return out
+
+
+def stream_length(c):
+    """floats of the reference's sample stream one call of case c consumes: 2 per sample, tasks in (source, triangle) order."""
+    F = SCENES[c['scene']]()[1].shape[0]
+    L = 1 if c['kind'] in ('vertex_gradient', 'sr_single') else (c.get('nsrc') or wall()[0].shape[0])
+    spp = 1 + (c['S'] - 1) // F
+    passes = 2 if c['kind'] == 'sr_gradient' else 1      # the first-generation gradient call draws its two passes from one stream
+    return 2 * L * F * spp * passes
+
+
 SCENES = {'ico': ico, 'ico2': ico2, 'field': field, 'occluder': occluder, 'backface': backface, 'bunny': scenes.bunny}
 
 
-def run_case(impl, oracle, c, seed=None, relabel=None):
+def run_case(impl, oracle, c, seed=None, relabel=None, ext_stream=None):
     """Run one case on `impl` (oracle / reference / gpu adapter: same function names as oracle.oracle).  `seed` is passed where the
     implementation takes one; `relabel` = (source permutation, face permutation) renders a relabelled copy of the same scene (how
-    independent draws are obtained from the reference, whose seed is fixed) and un-permutes the outputs.  Returns a dict of arrays."""
+    independent draws are obtained from the reference, whose seed is fixed) and un-permutes the outputs.  `ext_stream` (oracle only)
+    installs the reference's own (S,T) sample stream around the call under test — the "same-sample" cases.  Returns a dict of arrays."""
     o, n = wall(); v, f = SCENES[c['scene']]()
+    if c.get('nsrc'):
+        o, n = np.ascontiguousarray(o[:c['nsrc']]), np.ascontiguousarray(n[:c['nsrc']])
+
+    def call(fn, *a, **k):
+        if ext_stream is not None:
+            oracle.set_external_samples(ext_stream)
+        try:
+            return fn(*a, **k)
+        finally:
+            if ext_stream is not None:
+                oracle.set_external_samples(None)
     kw = {}
     if seed is not None:
         kw['seed'] = seed
@@ -132,10 +173,10 @@ def run_case(impl, oracle, c, seed=None, relabel=None):
     akw = {} if alpha is None else {'alpha': alpha}
     k = c['kind']
     if k == 'transient':
-        T = impl.transient(o_, n_, v, f_, c['S'], LB, UB, RES, c['rs'], c['sb'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)[0]
+        T = call(impl.transient, o_, n_, v, f_, c['S'], LB, UB, RES, c['rs'], c['sb'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)[0]
         return {'T': T[inv_s]}
     if k == 'intensity':
-        I = impl.intensity(o_, n_, v, f_, c['S'], LB, UB, vertex_normal=vn, **akw, **kw)
+        I = call(impl.intensity, o_, n_, v, f_, c['S'], LB, UB, vertex_normal=vn, **akw, **kw)
         return {'I': I[inv_f]}
     if k in ('gradient', 'scalar'):
         tkw = dict(akw)
@@ -143,37 +184,37 @@ def run_case(impl, oracle, c, seed=None, relabel=None):
             tkw['vertex_albedo'] = va
         if vn is not None:
             tkw['vertex_normal'] = vn
-        data = target(oracle, v, f, c['S'], **tkw); w = np.ones_like(data)
+        data = target(oracle, v, f, c['S'], nsrc=c.get('nsrc'), **tkw); w = np.ones_like(data)
         if k == 'gradient':
-            T, G, _ = impl.gradient(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], c['tf'], c['lf'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)
+            T, G, _ = call(impl.gradient, o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], c['tf'], c['lf'], vertex_normal=vn, vertex_albedo=va, **akw, **kw)
             return {'T': T[inv_s], 'G': G}
         if alpha is None:
-            T, g = impl.gradient_albedo(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], va, **kw)
+            T, g = call(impl.gradient_albedo, o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], va, **kw)
         else:
-            T, g = impl.gradient_alpha(o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], alpha, **kw)
+            T, g = call(impl.gradient_alpha, o_, n_, v, f_, c['S'], LB, UB, RES, data[sp], w, c['rs'], c['sb'], alpha, **kw)
         return {'g': np.array([g])}
     if k == 'vertex_gradient':
-        G = impl.vertex_gradient(c['vertex'], o[:1], n[:1], v, f_, c['S'], LB, UB, RES_VG, c['rs'], c['sb'], **kw)
+        G = call(impl.vertex_gradient, c['vertex'], o[:1], n[:1], v, f_, c['S'], LB, UB, RES_VG, c['rs'], c['sb'], **kw)
         return {'VG': np.asarray(G).reshape(-1, 3)}
     if k == 'sr_transient':
-        T = impl.sr_transient(o_, n_, v, f_, c['S'], LB, UB, RES, vertex_normal=vn, vertex_albedo=va, **kw)[0]
+        T = call(impl.sr_transient, o_, n_, v, f_, c['S'], LB, UB, RES, vertex_normal=vn, vertex_albedo=va, **kw)[0]
         return {'T': T[inv_s]}
     if k == 'sr_single':
         i = c['source']
-        return {'T': np.asarray(impl.sr_render_transient(o[i], n[i], v, f_, c['S'], LB, UB, RES, **kw)[0]).reshape(1, -1)}
+        return {'T': np.asarray(call(impl.sr_render_transient, o[i], n[i], v, f_, c['S'], LB, UB, RES, **kw)[0]).reshape(1, -1)}
     if k == 'sr_gradient':
         v2 = v.copy(); v2[:, 2] += 0.01
         data = oracle.sr_transient(o, n, v2, f, c['S'], LB, UB, RES, seed=5)[0]
-        T, G, _ = impl.sr_gradient(o_, n_, v, f_, c['S'], LB, UB, RES, c['w'], data[sp], **kw)
+        T, G, _ = call(impl.sr_gradient, o_, n_, v, f_, c['S'], LB, UB, RES, c['w'], data[sp], **kw)
         return {'T': T[inv_s], 'G': G}
     jw, jg = jitter_kernel()
     if k == 'jitter_transient':
-        T = impl.jitter_transient(o_, n_, v, f_, c['S'], LB, UB, RES, jw, c['offset'], vertex_normal=vn, **kw)[0]
+        T = call(impl.jitter_transient, o_, n_, v, f_, c['S'], LB, UB, RES, jw, c['offset'], vertex_normal=vn, **kw)[0]
         return {'T': T[inv_s]}
     if k == 'jitter_gradient':
         v2 = v.copy(); v2[:, 2] += 0.01
         data = oracle.jitter_transient(o, n, v2, f, c['S'], LB, UB, RES, jw, c['offset'], seed=5)[0]; w = np.ones_like(data)
-        T, G, _ = impl.jitter_gradient(o_, n_, v, f_, c['S'], LB, UB, RES, jw, jg, c['offset'], data[sp], w, c['tf'], **kw)
+        T, G, _ = call(impl.jitter_gradient, o_, n_, v, f_, c['S'], LB, UB, RES, jw, jg, c['offset'], data[sp], w, c['tf'], **kw)
         return {'T': T[inv_s], 'G': G}
     raise KeyError(k)
 

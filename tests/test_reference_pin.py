@@ -5,7 +5,9 @@ stand-in headers of oracle/ref_shim by `make -C oracle ref`, run by tools/make_r
 deviation over R independent reference renders.  The reference samples with per-thread Mersenne Twisters, this repository with a
 counter-based generator, so stochastic outputs are compared with a two-sample z test per element (K renders with different seeds on
 this side); what that resolves is printed as `rel` (the relative L2 distance of the two means, a few 1e-3).  Deterministic entry
-points (regularisers, ray queries) are compared directly.
+points (regularisers, ray queries) are compared directly.  SAME-SAMPLE cases go further: the fixture also holds the (S,T) stream one
+reference worker draws (`same/stream`), the oracle is run on exactly those samples, and every entry point must then reproduce the
+reference's output to float rounding (measured 2e-7 ... 5e-6).
 
 Acceptance (stated here, used below), over the n elements with spread:  rms(z) <= 1.30 + 2.5/sqrt(n),  |mean(z)| <= 0.20 + 2/sqrt(n),
 max|z| <= 10, and the two means within 3 % in L2 or within 1.5x the distance Monte-Carlo noise alone produces (cases with fewer than
@@ -63,6 +65,29 @@ def test_oracle_matches_reference_statistically(name, oracle):
         if draws[0][key] is None:
             continue
         check(name, key, fx['%s/%s/mean' % (name, key)], fx['%s/%s/std' % (name, key)], R, [x[key] for x in draws])
+
+
+SAME = rc.same_sample_cases()
+# Same samples -> same numbers up to float rounding (the reference is plain -O2 code, the oracle pins an fma order): 1e-7 ... 5e-6
+# wherever no sample changes bin.  A last-bit difference in r does move a sample to the neighbouring bin now and then — about one sample
+# in 5e4 for the 4.8 mm bins, ten times as often for the refine_scale = 10 fine bins that smoothed transients and all gradients use —
+# and with only 20 samples per triangle each such sample weighs ~5e-5 of the output norm.  Hence two bars: raw-histogram outputs 1e-4,
+# outputs built on fine bins 5e-4.  (A wrong formula, constant or index shows up at 1e-2 ... 1.)
+TOL_SAME = {'T': 1e-4, 'I': 2e-5, 'G': 5e-4, 'g': 5e-4, 'VG': 5e-4}
+
+
+@pytest.mark.parametrize('name', sorted(SAME))
+def test_oracle_matches_reference_on_the_reference_sample_stream(name, oracle):
+    """The oracle run on the (S,T) stream the reference's own single-worker run consumed: agreement to rounding, entry point by entry point."""
+    fx = fixture(); c = SAME[name]
+    stream = fx['same/stream'][:rc.stream_length(c)]
+    got = rc.run_case(rc.OracleAdapter(oracle), oracle, c, ext_stream=stream)
+    for key, val in got.items():
+        want = fx['same/%s/%s' % (name, key)]
+        err = np.linalg.norm(val - want) / max(np.linalg.norm(want), 1e-300)
+        print('same/%s/%s rel %.2e' % (name, key, err))
+        tol = 5e-4 if (key == 'T' and c.get('rs', 1) > 1 and c['kind'] == 'transient') else TOL_SAME[key]
+        assert np.linalg.norm(want) > 0 and err <= tol, (name, key, err)
 
 
 def test_regularisers_match_reference(oracle):

@@ -7,7 +7,7 @@ copies of each scene (random permutations of the source order and of the face or
 fixture stores the per-element mean and standard deviation over the R draws.  Deterministic entry points are stored as they are.
 
     python tools/make_ref_fixtures.py            # everything, ~8 minutes (the reference's gradient tap loop is slow)
-    python tools/make_ref_fixtures.py NAME...    # regenerate the named cases only and merge into the existing file
+    python tools/make_ref_fixtures.py NAME...    # regenerate the named cases only (also: `same`, `deterministic`) and merge into the existing file
 """
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
@@ -46,6 +46,19 @@ def main():
             out['%s/%s/mean' % (name, key)] = d.mean(0)
             out['%s/%s/std' % (name, key)] = d.std(0, ddof=1)
         print('%-24s %.1fs' % (name, time.time() - t0), flush=True)
+        np.savez_compressed(OUT, **out)
+    if not only or 'same' in only:
+        # same-sample cases: ONE reference worker, no relabelling -> the sample stream is worker 0's, stored once for all cases
+        reference.set_threads(1)
+        cases = rc.same_sample_cases()
+        out['same/stream'] = reference.sampler_stream(max(rc.stream_length(c) for c in cases.values()))
+        for name, c in cases.items():
+            t0 = time.time()
+            res = rc.run_case(reference, oracle, c)
+            for key, val in res.items():
+                assert np.isfinite(val).all(), (name, key)
+                out['same/%s/%s' % (name, key)] = val
+            print('same/%-24s %.1fs' % (name, time.time() - t0), flush=True)
         np.savez_compressed(OUT, **out)
     if only and 'deterministic' not in only:
         return
