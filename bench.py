@@ -107,9 +107,36 @@ def cpu_baseline(v, f, n_sources, want_stats=True, repeats=1):
     return samples / min(times), oracle.threads(), times, stats
 
 
+def reference_build_rate(v, f, n_sources=32):
+    """Throughput of the reference's OWN translation units (oracle/_ref, built against the stand-in Embree/TBB/MKL/Boost headers) on a
+    small sample, for the record: its ray query is the stand-in's scalar BVH, so it is SLOWER than the port and not used as the arm."""
+    try:
+        from oracle import oracle, reference
+        if not reference.available():
+            return None
+        from nlos_surface_optimization_b200 import scenes
+        o, n = scenes.wall_grid(WALL)
+        idx = np.linspace(0, o.shape[0] - 1, n_sources).astype(int)
+        o = np.ascontiguousarray(o[idx]); n = np.ascontiguousarray(n[idx])
+        B = oracle.num_bins(LB, UB, RES)
+        data = np.zeros((n_sources, B)); weight = np.ones((n_sources, B))
+        reference.set_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        reference.gradient(o, n, v, f, SAMPLE_NUM, LB, UB, RES, data, weight, REFINE, SIGMA, 1, 0)
+        dt = time.perf_counter() - t0
+        spp = 1 + (SAMPLE_NUM - 1) // f.shape[0]
+        return {'value': 2 * n_sources * f.shape[0] * spp / dt, 'unit': UNIT, 'sample': '%d wall points, %.1f s' % (n_sources, dt),
+                'note': "the reference's unmodified sources on stand-in library headers (oracle/ref_shim): scalar double-precision ray query instead of "
+                        "Embree, so slower than the port above; reported for transparency, not used for the ratio"}
+    except Exception as e:     # the arm must not fail because the optional build is absent or broken
+        return {'unavailable': str(e)[:200]}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Embree/MKL build cannot be made
-    here) on the host cores, each step a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, each step a bounded sample of the workload.
+    The arm is the oracle port: of the two CPU implementations available (the port, and the reference's own sources compiled against
+    stand-in library headers, oracle/_ref) it is the FASTER one — the conservative choice for a GPU/CPU ratio; the other is reported
+    under `reference_build`."""
     if rank != 0:
         return
     from nlos_surface_optimization_b200 import scenes
@@ -130,6 +157,9 @@ def run_reference(args, rank):
                              'sample': '%d of 4096 wall points x all 69630 triangles, forward+gradient, OpenMP oracle (reference-restated CPU path, not the Embree build)' % n_src},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'ms_per_iteration_extrapolated': 1e3 * (2 * 4096 * f.shape[0] * spp) / value}
+    rb = reference_build_rate(v, f)
+    if rb is not None:
+        line['reference_build'] = rb
     print(json.dumps(line))
 
 
