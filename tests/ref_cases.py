@@ -102,6 +102,7 @@ CASES = {
     'jitter_transient_sh':  dict(kind='jitter_transient', scene='ico', S=S, offset=8, shading=True),
     'jitter_gradient_t1':   dict(kind='jitter_gradient', scene='ico', S=S, offset=8, tf=1),
     'jitter_gradient_t0':   dict(kind='jitter_gradient', scene='occluder', S=S, offset=8, tf=0),
+    'jitter_gradient_off3': dict(kind='jitter_gradient', scene='ico', S=S, offset=3, tf=1),
     # the headline mesh (69 630 triangles, real self-occlusion), 2 samples per triangle and source
     'bunny_transient':      dict(kind='transient', scene='bunny', S=2 * 69630, rs=10, sb=1),
     'bunny_gradient':       dict(kind='gradient', scene='bunny', S=2 * 69630, rs=10, sb=1, tf=1, lf=0),
