@@ -59,9 +59,9 @@ __device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGe
 //   phase A (generate): lane <-> triangle.  Every lane draws the sample of the next slot (slot = source*spp + k), runs
 //     the self intersection and the shading that needs no visibility; samples that can contribute (front-facing, in
 //     range) are COMPACTED into a per-warp ray queue in shared memory (ballot + popc).
-//   phase B (trace): whenever 32 rays are queued (or the slots are exhausted) each lane pops one ray — of any triangle
-//     of the tile — and runs the any-hit traversal; visible rays add their value to the transient row (FP64 RED) and
-//     set their bit in the warp's visibility tile.
+//   phase B (trace): idle lanes pop rays — of any triangle of the tile — from the queue (refilled whenever kRefill lanes are
+//     idle) and run the any-hit traversal; visible rays add their value to the transient row (FP64 RED) and set their bit in
+//     the warp's visibility tile.
 // Back-facing / out-of-range samples therefore never occupy a lane during traversal, which is where the time goes.
 constexpr int kQCap = 64;        // ray queue capacity per warp (power of two, >= 63)
 constexpr int kTile = 256;       // sample slots per warp pass == visibility words in the warp tile
