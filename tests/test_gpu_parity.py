@@ -418,6 +418,24 @@ def test_first_generation_api(oracle, gpu_ctx):
     assert rel_l2(T, T_st) <= TOL_TRANSIENT
 
 
+def test_zero_area_triangles(oracle, gpu_ctx):
+    """Coincident / collinear vertices: such triangles cannot be hit, so they contribute nothing — on both sides, without NaNs."""
+    from nlos_surface_optimization_b200 import renderer, scenes
+    o, n = scenes.wall_grid(3)
+    v, f = scenes.fan8()
+    v = np.ascontiguousarray(np.vstack([v, [[0.1, 0.1, 0.3], [0.1, 0.1, 0.3], [0.2, 0.1, 0.3], [0.3, 0.1, 0.3]]]), dtype=np.float32)
+    f = np.ascontiguousarray(np.vstack([f, [[9, 10, 11]], [[10, 11, 12]]]), dtype=np.int32)
+    ns = 4 * f.shape[0]
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1, 1, 0)
+    B = T_ref.shape[1]
+    T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+    assert np.isfinite(T).all() and np.isfinite(G).all()
+    assert rel_l2(T, T_ref) <= TOL_TRANSIENT and rel_l2(G, G_ref) <= TOL_GRADIENT
+    assert np.all(G[9:] == 0)
+
+
 def test_sharded_rendering_nccl_two_gpus(oracle, tmp_path):
     """dist.inverse_rendering_sharded over NCCL on 2 GPUs (skipped on a 1-GPU box): all-reduced gradient and gathered
     transient equal the single-GPU call."""
