@@ -275,7 +275,10 @@ __global__ void k_box_filter(const double* __restrict__ in, double* __restrict__
 // ---------------------------------------------------------------------------------------------- K4/K5 gradients
 // KIND 0: vertex gradient (9 FP64 register accumulators per thread), 1: albedo scalar, 2: GGX alpha scalar
 template <bool GGX, bool HAS_VN, bool HAS_VA, int KIND, bool USE_VIS>
-__global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
+#ifndef NLOS_GRAD_MINBLOCKS
+#define NLOS_GRAD_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kBlock, NLOS_GRAD_MINBLOCKS) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
                                                      const uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
                                                      const double* __restrict__ dprefix, double* __restrict__ out) {
   extern __shared__ double s_tab[];         // [0..K] prefix of w_i, [K+1..2K+1] prefix of w_i*delta_i

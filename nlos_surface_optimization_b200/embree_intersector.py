@@ -71,6 +71,16 @@ class PyMesh(object):
         self.v, self.f, self.ctx = v, f, ctx
         self.vn = self.fn = self.face_area = None
 
+    def test(self):
+        """embree_intersector.pyx:14 / c_mesh.cpp:50-59: print the vertex and face tables."""
+        import numpy as np
+        print("vertices")
+        for p in np.asarray(self.v):
+            print("%f %f %f" % (p[0], p[1], p[2]))
+        print("faces")
+        for t in np.asarray(self.f):
+            print("%d %d %d " % (t[0], t[1], t[2]))
+
     def embree3_tbb_intersection(self, origin, direction, barycoord):
         embree3_tbb_intersection(origin, direction, self.v, self.f, barycoord, ctx=self.ctx)
 

@@ -10,3 +10,4 @@ wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $OUT/libnlos_$1.so $OUT/obj_$1/*.o -lcudart
 grep -A1 "k_forwardILb0ELb0ELb0ELb0ELb1ELi0" $OUT/obj_$1/render_kernels.log | grep -o "Used [0-9]* registers" | head -1
 grep -A1 "k_forwardILb0ELb0ELb0ELb0ELb1ELi0" $OUT/obj_$1/render_kernels.log | grep -o "[0-9]* bytes spill stores" | head -1
+grep -A1 "k_gradientILb0ELb0ELb0ELi0ELb1E" $OUT/obj_$1/render_kernels.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | head -2
