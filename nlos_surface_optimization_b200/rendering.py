@@ -1,8 +1,9 @@
 """Facade with the names and return values of the reference's exp_bunny/rendering.py:219-308 — the thin
 callers of the renderer boundary that every optimisation loop uses (exp_bunny/test.py:161-170).
 
-Only the functions ON the hot path are mirrored; remeshing / projection helpers of the reference file
-(:32-206, CGAL / El Topo / Embree-intersector / pyigl) stay in the reference and are untouched.  `mesh` and
+The functions that sit directly on the renderer / intersector boundary are mirrored (plus the small NumPy loss helpers the
+loops call next to them); the remeshing helpers of the reference file (:32-180, CGAL / El Topo / pyigl) stay in the reference
+and are untouched.  `mesh` and
 `opt` are the reference's ad-hoc objects (attributes v, f, vn, alpha, albedo, f_affinity / lighting,
 lighting_normal, sample_num, max_distance_bin, distance_resolution, bin_refine_resolution, sigma_bin,
 testing_flag, loss_flag, alpha_flag, albedo_flag, jitter, normal).
@@ -10,6 +11,10 @@ testing_flag, loss_flag, alpha_flag, albedo_flag, jitter, normal).
 import numpy as np
 
 from . import renderer, ggx
+
+__all__ = ['create_weighting_function', 'inverseShadingRendering', 'inverseRenderingAlpha', 'inverseRenderingAlbedo', 'inverseRendering',
+           'removeTriangle', 'forwardRendering', 'renderStreamedNormalSmoothing', 'renderStreamedCurvatureGradient', 'vertex_gradient',
+           'space_carving_projection', 'face_normal_and_area', 'evaluate_loss_with_normal_smoothness', 'evaluate_loss_with_curvature']
 
 
 def _bounds(opt):
@@ -154,3 +159,44 @@ def evaluate_loss_with_normal_smoothness(gt_transient, weight, transient, smooth
     L1 = np.linalg.norm(difference) ** 2 / difference.shape[0]
     L2 = render_opt.smooth_weight * smoothing_val
     return L1 + L2, L1
+
+
+def vertex_gradient(mesh, vertex_num, opt):
+    """:26-30 per-bin gradient of one vertex (debug / figure helper)."""
+    gradient = np.zeros((opt.max_distance_bin, 3), dtype=np.double, order='C')
+    lo, hi, res = _bounds(opt)
+    renderer.renderStreamedVertexGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, res, gradient, vertex_num,
+                                          opt.bin_refine_resolution, opt.sigma_bin)
+    return gradient
+
+
+def space_carving_projection(v, space_carving_mesh):
+    """:193-206 push vertices that lie in front of the space-carving hull back onto it: one +z ray per vertex from the wall plane
+    against the hull (embree_intersector on the LBVH), in place on v[:, 2]."""
+    from . import embree_intersector
+    direction = np.tile(np.array([0, 0, 1], dtype=np.float32), (v.shape[0], 1))
+    barycoord = np.zeros((v.shape[0], 3), dtype=np.float32, order='C')
+    foot = np.array(v, dtype=np.float32, order='C')
+    foot[:, 2] = 0
+    embree_intersector.embree3_tbb_intersection(foot, direction, space_carving_mesh.v, space_carving_mesh.f, barycoord)
+    intersection_p = np.zeros((v.shape[0], 3), dtype=np.float32, order='C')
+    embree_intersector.barycoord_to_world(space_carving_mesh.v, space_carving_mesh.f, barycoord, intersection_p)
+    hit = barycoord[:, 0] >= 0
+    v[hit, 2] = np.maximum(intersection_p[hit, 2], v[hit, 2])
+
+
+def face_normal_and_area(v, f):
+    """:310-318 (pure NumPy; the epsilon keeps degenerate faces finite, as in the reference)."""
+    import sys
+    n = np.cross(v[f[:, 1], :] - v[f[:, 0], :], v[f[:, 2], :] - v[f[:, 0], :], axis=1)
+    n = n + sys.float_info.epsilon
+    d = np.linalg.norm(n, axis=1)
+    return n / d[:, None], d / 2
+
+
+def evaluate_loss_with_curvature(gt_transient, weight, transient, mesh, render_opt):
+    """:369-380 (pure NumPy): weighted L2 + smooth_weight * total surface area."""
+    difference = (transient - gt_transient) * np.sqrt(weight)
+    L1 = np.linalg.norm(difference) ** 2 / difference.shape[0]
+    total_area = float(np.sum(face_normal_and_area(mesh.v, mesh.f)[1]))
+    return L1 + render_opt.smooth_weight * total_area, L1, total_area

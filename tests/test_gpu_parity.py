@@ -436,6 +436,28 @@ def test_zero_area_triangles(oracle, gpu_ctx):
     assert np.all(G[9:] == 0)
 
 
+def test_facade_helpers_on_the_boundary(oracle, gpu_ctx):
+    """exp_bunny/rendering.py helpers that call the boundary directly: vertex_gradient (:26-30) and space_carving_projection (:193-206)."""
+    from nlos_surface_optimization_b200 import rendering, scenes
+
+    class Obj(object):
+        pass
+    o, n = scenes.wall_grid(1)
+    mesh = Obj(); mesh.v, mesh.f = scenes.icosphere(2, 0.1, (0.0, 0.0, 0.45))
+    opt = Obj(); opt.lighting, opt.lighting_normal = o, n
+    opt.max_distance_bin, opt.distance_resolution, opt.sample_num, opt.bin_refine_resolution, opt.sigma_bin = 1200, 1.2e-3, 50 * mesh.f.shape[0], 10, 1
+    g = rendering.vertex_gradient(mesh, 3, opt)
+    g_ref = oracle.vertex_gradient(3, o, n, mesh.v, mesh.f, opt.sample_num, 0.0, 1.44, 1.2e-3, 10, 1)
+    assert np.linalg.norm(g_ref) > 0 and rel_l2(g, g_ref) <= TOL_GRADIENT
+    # space carving: a flat hull at z = 0.4 over x,y in [-0.1, 0.1]; vertices in front of it are pushed back to 0.4, others stay
+    hull = Obj(); hull.v, hull.f = scenes.quad(0.4, 0.1)
+    v = np.array([[0.0, 0.0, 0.3], [0.05, -0.05, 0.5], [0.3, 0.3, 0.2]], dtype=np.float32)
+    rendering.space_carving_projection(v, hull)
+    assert np.allclose(v[:, 2], [0.4, 0.5, 0.2], atol=1e-6)
+    nrm, area = rendering.face_normal_and_area(hull.v, hull.f)
+    assert np.allclose(area, 0.02, rtol=1e-5) and np.allclose(np.abs(nrm[:, 2]), 1.0, atol=1e-6)
+
+
 def test_sharded_rendering_nccl_two_gpus(oracle, tmp_path):
     """dist.inverse_rendering_sharded over NCCL on 2 GPUs (skipped on a 1-GPU box): all-reduced gradient and gathered
     transient equal the single-GPU call."""
