@@ -56,6 +56,12 @@ int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value);
 /* ms of the last call: {scene build, forward, residual, gradient, total}; needs option "timing" = 1 */
 int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5);
 uint64_t nlos_ctx_launch_count(nlos_ctx* ctx);         /* kernels launched through this context so far */
+/* TEST HOOK (no reference counterpart): replace the counter-based generator by an external stream of (S,T) pairs, n floats (host or
+ * device pointer, copied); sample k of (global source s, triangle f) reads st[2*((s*numTriangles + f)*spp + k)] — the order in which
+ * one worker of the reference consumes its Mersenne-Twister stream (sampler.cpp:20-33, transient_and_gradient.cpp:184-186), so that
+ * outputs can be compared with the reference's own sample for sample.  n = 0 restores the generator.  Not honoured by
+ * nlos_streamed_render_vertex_gradient (the reference skips non-adjacent triangles there before drawing). */
+int nlos_ctx_set_external_samples(nlos_ctx* ctx, const float* st, int64_t n);
 
 /* ---- module `renderer` (smoothed_transient/) ----------------------------------------------------- */
 

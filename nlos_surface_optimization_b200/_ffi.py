@@ -39,6 +39,7 @@ SIGNATURES = {
     'nlos_ctx_set_option': (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     'nlos_ctx_get_timing': (C.c_int, [_ctx, _f]),
     'nlos_ctx_launch_count': (C.c_uint64, [_ctx]),
+    'nlos_ctx_set_external_samples': (C.c_int, [_ctx, _f, C.c_int64]),
     'nlos_streamed_render_transient': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                                  _d, _d, C.c_int, C.c_int, C.c_int]),
     'nlos_streamed_render_intensity': (C.c_int, [_ctx, _f, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, C.c_int, C.c_float, C.c_float, _d]),
@@ -118,6 +119,15 @@ class Context(object):
 
     def set_source_window(self, src_offset, num_sources_global):
         self.check(self.lib.nlos_ctx_set_source_window(self.handle, int(src_offset), int(num_sources_global)), 'nlos_ctx_set_source_window')
+
+    def set_external_samples(self, stream):
+        """TEST HOOK: draw the (S,T) pairs from `stream` (float32 array, or None to restore the generator); see include/nlos_b200.h."""
+        if stream is None:
+            self.check(self.lib.nlos_ctx_set_external_samples(self.handle, None, 0), 'nlos_ctx_set_external_samples')
+            return
+        import numpy as np
+        a = np.ascontiguousarray(stream, dtype=np.float32)
+        self.check(self.lib.nlos_ctx_set_external_samples(self.handle, a.ctypes.data_as(_f), a.size), 'nlos_ctx_set_external_samples')
 
     def set_option(self, key, value):
         self.check(self.lib.nlos_ctx_set_option(self.handle, key.encode(), int(value)), 'nlos_ctx_set_option(%s)' % key)

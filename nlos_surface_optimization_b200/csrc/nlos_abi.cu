@@ -117,6 +117,11 @@ int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forwa
 
 void run_job(Ctx& cx, const Job& j_in) {
   Job j = j_in;
+  // sample kernels: the production build, or (test hook active) the build that reads the external (S,T) stream
+  const bool use_ext = cx.ext_count > 0;
+  auto fwd = use_ext ? ext::launch_forward : launch_forward;
+  auto inten = use_ext ? ext::launch_intensity : launch_intensity;
+  auto grad = use_ext ? ext::launch_gradient : launch_gradient;
   if (j.sr && j.kind == 0) {
     // the first-generation gradient is the tabulated-kernel path with the unit kernel: A[b] = -2 diff[b], B[b] = 0
     static const double kOne = 1.0, kZero = 0.0;
@@ -186,6 +191,8 @@ void run_job(Ctx& cx, const Job& j_in) {
     if (j.kind == 3 || j.jlen > 0) P.r_fwd = 1;                                          // jitter: coarse histogram, then tabulated conv
     P.res_fwd = j.res / P.r_fwd;                                                         // TG.cpp:313
     P.alpha = j.alpha; P.testing_flag = j.testing_flag; P.sr = j.sr;
+    P.F = j.F;
+    if (cx.ext_count > 0) { P.ext_samples = cx.buf("ext_samples").as<float>((size_t)cx.ext_count); P.ext_count = cx.ext_count; }
     P.words_per_row = (j.F + 31) / 32;
     TapTables taps;
     if (j.kind != 3) {
@@ -204,7 +211,7 @@ void run_job(Ctx& cx, const Job& j_in) {
 
     if (j.kind == 3) {
       P.chunk = forward_chunk(cx);
-      launch_intensity(cx, sc, P, j.ggx, o_I.dev);
+      inten(cx, sc, P, j.ggx, o_I.dev);
       if (timing) { NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[4], st)); }
     } else {
       // ---- K1: forward (+ visibility bits for the gradient pass)
@@ -219,10 +226,10 @@ void run_job(Ctx& cx, const Job& j_in) {
         d_jg = stage_in(cx, "in_jg", j.jg, (size_t)j.jlen, st);
         double* hist = cx.buf("jit_hist").as<double>(LB);
         NLOS_CUDA_OK(cudaMemsetAsync(hist, 0, LB * sizeof(double), st));
-        launch_forward(cx, sc, P, j.ggx, hist, vis, d_wprefix);
+        fwd(cx, sc, P, j.ggx, hist, vis, d_wprefix);
         launch_jitter_conv(cx, hist, d_jw, j.jlen, j.joff, j.numBins, j.L, o_T.dev);
       } else
-      launch_forward(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
+      fwd(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
       if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st));
       NLOS_CUDA_OK(cudaEventRecord(cx.ev_fwd, st)); fwd_recorded = true;        // the transient is final here
       if (want_grad) {
@@ -249,16 +256,17 @@ void run_job(Ctx& cx, const Job& j_in) {
           launch_jitter_tables(cx, diff, d_jw, d_jg, j.jlen, j.joff, j.numBins, j.L, jA, jB);
           P.jitter = 1; P.jA = jA; P.jB = jB;
         }
+        if (j.sr && P.ext_samples) P.ext_base = 2 * (cx.num_sources_global > 0 ? cx.num_sources_global : j.L) * (int64_t)j.F * P.spp;   // SR/SSG.cpp:400-470: one sampler set for both passes
         if (j.kind == 0) {
           double* acc = cx.buf("grad_acc").as<double>(3 * (size_t)j.V);
           NLOS_CUDA_OK(cudaMemsetAsync(acc, 0, 3 * (size_t)j.V * sizeof(double), st));
-          launch_gradient(cx, sc, P, j.ggx, 0, diff, vis, d_wprefix, d_dprefix, acc);
+          grad(cx, sc, P, j.ggx, 0, diff, vis, d_wprefix, d_dprefix, acc);
           if (j.sr) NLOS_CUDA_OK(cudaMemsetAsync(o_G.dev, 0, 3 * (size_t)j.V * sizeof(double), st));   // SR/SSG.cpp:414: cleared, not accumulated
           launch_finalize_gradient(cx, acc, o_G.dev, 3 * (size_t)j.V, 1.0 / (double)Lnorm);
         } else {
           double* acc = cx.buf("scalar_acc").as<double>(1);
           NLOS_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double), st));
-          launch_gradient(cx, sc, P, j.ggx, j.kind, diff, vis, d_wprefix, d_dprefix, acc);
+          grad(cx, sc, P, j.ggx, j.kind, diff, vis, d_wprefix, d_dprefix, acc);
           double h = 0;
           NLOS_CUDA_OK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, st));
           NLOS_CUDA_OK(cudaStreamSynchronize(st));
@@ -356,6 +364,23 @@ int nlos_ctx_synchronize(nlos_ctx* ctx) {
 }
 void* nlos_ctx_stream(nlos_ctx* ctx) { return ctx ? (void*)ctx->cx.stream : nullptr; }
 int nlos_ctx_set_seed(nlos_ctx* ctx, uint64_t seed) { if (!ctx) return NLOS_ERR_INVALID; ctx->cx.seed = seed; return NLOS_OK; }
+int nlos_ctx_set_external_samples(nlos_ctx* ctx, const float* st, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && !st)) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_CUDA_OK(cudaStreamSynchronize(cx.stream));
+    cx.ext_count = 0;
+    if (n > 0) {
+      float* d = cx.buf("ext_samples").as<float>((size_t)n);
+      NLOS_CUDA_OK(cudaMemcpyAsync(d, st, (size_t)n * sizeof(float), cudaMemcpyDefault, cx.stream));
+      NLOS_CUDA_OK(cudaStreamSynchronize(cx.stream));
+      cx.ext_count = n;
+    }
+    cx.last_error.clear(); return NLOS_OK;
+  } catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
 int nlos_ctx_set_source_window(nlos_ctx* ctx, int64_t src_offset, int64_t num_sources_global) {
   if (!ctx || src_offset < 0 || num_sources_global < 0) return NLOS_ERR_INVALID;
   ctx->cx.src_offset = src_offset; ctx->cx.num_sources_global = num_sources_global; return NLOS_OK;

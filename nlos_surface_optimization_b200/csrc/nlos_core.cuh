@@ -396,8 +396,7 @@ struct SampleGeom { f3 d; float u, v, w, r, t; };
 
 // generate the sample point / ray direction (TG.cpp:184-195) and run the self intersection that yields
 // the hit barycentrics the reference reads back from Embree (TG.cpp:208-212).
-NLOS_HD bool sample_self_hit(uint64_t seed, int64_t src_global, int prim, int k, f3 o, const ShadeTri& st, const TriRec& tr, SampleGeom& g) {
-  float S, T; sample_ST(seed, src_global, prim, k, S, T);
+NLOS_HD bool sample_self_hit_st(float S, float T, f3 o, const ShadeTri& st, const TriRec& tr, SampleGeom& g) {
   const float sqrtT = sqrtf(T);
   const float u = 1 - sqrtT, v = (1 - S) * sqrtT, w = S * sqrtT;
   const f3 point = blend3(u, st.v1, v, st.v2, w, st.v3);
@@ -410,6 +409,10 @@ NLOS_HD bool sample_self_hit(uint64_t seed, int64_t src_global, int prim, int k,
   const f3 pt = blend3(g.u, st.v1, g.v, st.v2, g.w, st.v3);
   g.r = len3(pt - o);
   return true;
+}
+NLOS_HD bool sample_self_hit(uint64_t seed, int64_t src_global, int prim, int k, f3 o, const ShadeTri& st, const TriRec& tr, SampleGeom& g) {
+  float S, T; sample_ST(seed, src_global, prim, k, S, T);
+  return sample_self_hit_st(S, T, o, st, tr, g);
 }
 
 // tap -> coarse-bin grouping shared by the smoothed forward splat and the gradient (DESIGN.md "K-tap

@@ -43,6 +43,7 @@ struct Ctx {
   int64_t src_offset = 0;        // global index of the first source of this call (sharded runs)
   int64_t num_sources_global = 0;  // 0 => normalise the gradient by this call's L (reference behaviour)
   int reuse_visibility = 1;      // gradient pass consumes the forward pass's visibility bits
+  int64_t ext_count = 0;         // test hook: floats of the external (S,T) sample stream held in buf("ext_samples"), 0 = Philox
   int timing_enabled = 0;
   int chunk_forward = 0;         // sources per blockIdx.y in the forward pass (0 = auto)
   int chunk_gradient = 0;        // same for the gradient pass

@@ -51,6 +51,10 @@ struct RenderParams {
   const double* jA;         // sum_i jitter_weight[i] * (-2) diff[s, b+i-offset]
   const double* jB;         // sum_i jitter_grad[i]   * (-2) diff[s, b+i-offset]
   double grad_coef;         // factor of the kernel-derivative term: 2/sigma^2 (Gaussian) or -2/res (jitter/TG.cpp:950)
+  // test hook (nlos_ctx_set_external_samples): when non-null the (S,T) pair of sample k of (global source s, triangle f) is read from
+  // ext_samples[ext_base + 2*((s*F + f)*spp + k)] instead of being drawn from Philox — the order in which ONE worker of the reference
+  // consumes its stream, so the CUDA path can be compared with the reference's own outputs sample for sample
+  const float* ext_samples; int64_t ext_count; int64_t ext_base; int F;
   int sr;                   // 1: first-generation renderer (stratified_transient_raytracer/): forward without the form-factor clamp
                             //    (SR/SST.cpp:130-137), gradient with the normal-variation term always on (SR/SSG.cpp:266-271)
 };

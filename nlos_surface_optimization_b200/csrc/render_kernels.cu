@@ -19,6 +19,9 @@
 #include "render_kernels.h"
 
 namespace nlos {
+#ifdef NLOS_EXT_BUILD      // second build of this file (render_kernels_ext.cu): the same kernels with the external-sample test hook compiled in
+namespace ext {
+#endif
 
 namespace {
 
@@ -53,6 +56,19 @@ template <bool HAS_VN>
 __device__ __forceinline__ f3 shading_normal(const TriRegs& t, const SampleGeom& g) { return HAS_VN ? blend3(g.u, t.n1, g.v, t.n2, g.w, t.n3) : t.st.nf; }
 template <bool HAS_VA>
 __device__ __forceinline__ float shading_albedo(const TriRegs& t, const SampleGeom& g) { return HAS_VA ? blend1(g.u, t.a1, g.v, t.a2, g.w, t.a3) : 1.0f; }
+
+// The two uniforms of sample k of (global source s, triangle prim): Philox.  In the SECOND build of this file (NLOS_EXT_BUILD,
+// namespace nlos::ext, selected by run_job only while nlos_ctx_set_external_samples is active) they come from the external stream
+// of the test hook instead — compiled separately because even a never-taken branch costs the production kernel 3-4 % (registers).
+__device__ __forceinline__ bool draw_sample(const RenderParams& P, int64_t src_global, int prim, int k, f3 o, const ShadeTri& st, const TriRec& tr, SampleGeom& g) {
+#ifdef NLOS_EXT_BUILD
+  const int64_t idx = P.ext_base + 2 * ((src_global * (int64_t)P.F + prim) * P.spp + k);
+  if (P.ext_samples == nullptr || idx < 0 || idx + 1 >= P.ext_count) return false;
+  return sample_self_hit_st(__ldg(P.ext_samples + idx), __ldg(P.ext_samples + idx + 1), o, st, tr, g);
+#else
+  return sample_self_hit(P.seed, src_global, prim, k, o, st, tr, g);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------- K1 forward
 // Warp-level two-phase kernel (DESIGN.md "Forward kernel"):
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
                        dot3(on, w2) > 1e-5f * (fabsf(w2.x) + fabsf(w2.y) + fabsf(w2.z)) &&
                        dot3(on, w3) > 1e-5f * (fabsf(w3.x) + fabsf(w3.y) + fabsf(w3.z));
             }
-            if (!culled && sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
+            if (!culled && draw_sample(P, P.src_offset + s, t.prim, k, o, t.st, t.tr, g) && g.r <= ub_half && g.r >= lb_half) {
               const f3 n = shading_normal<HAS_VN>(t, g);
               const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
               if (P.sr ? ff != 0.0f : ff > 0.0f) {                                  // max(0,ff)==0 adds exactly 0 (TG.cpp:228); SR has no clamp
@@ -275,10 +291,7 @@ __global__ void k_box_filter(const double* __restrict__ in, double* __restrict__
 // ---------------------------------------------------------------------------------------------- K4/K5 gradients
 // KIND 0: vertex gradient (9 FP64 register accumulators per thread), 1: albedo scalar, 2: GGX alpha scalar
 template <bool GGX, bool HAS_VN, bool HAS_VA, int KIND, bool USE_VIS>
-#ifndef NLOS_GRAD_MINBLOCKS
-#define NLOS_GRAD_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(kBlock, NLOS_GRAD_MINBLOCKS) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
+__global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
                                                      const uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
                                                      const double* __restrict__ dprefix, double* __restrict__ out) {
   extern __shared__ double s_tab[];         // [0..K] prefix of w_i, [K+1..2K+1] prefix of w_i*delta_i
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(kBlock, NLOS_GRAD_MINBLOCKS) k_gradient(const 
       const float4 o4 = __ldg(P.origin + s), n4 = __ldg(P.onormal + s);
       const f3 o = xyz(o4), on = xyz(n4);
       SampleGeom g;
-      if (!sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) continue;
+      if (!draw_sample(P, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) continue;
       if (!(g.r <= ub_half && g.r >= lb_half)) continue;
       const f3 n = shading_normal<HAS_VN>(t, g);
       const f3 d = g.d; const float hl = g.r;
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(kBlock) k_visibility(const DeviceScene sc, con
     const f3 o = xyz(__ldg(P.origin + s));
     for (int k = 0; k < P.spp; ++k) {
       SampleGeom g; uint8_t bit = 0;
-      if (sample_self_hit(P.seed, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) {
+      if (draw_sample(P, P.src_offset + s, t.prim, k, o, t.st, t.tr, g)) {
         const Ray ray = make_ray(o, g.d);
         uint32_t cb = 0, ct = 0;
         bit = occluded(sc.nodes, sc.ttris, sc.root_count, ray, g.t, t.prim, &cb, &ct) ? 0 : 1;
@@ -613,4 +626,7 @@ void launch_pathlengths(Ctx& cx, double* pl, int B, float lb, float res) {
   NLOS_CUDA_OK(cudaGetLastError());
 }
 
+#ifdef NLOS_EXT_BUILD
+}  // namespace ext
+#endif
 }  // namespace nlos

@@ -22,4 +22,11 @@ void launch_ray_query(Ctx& cx, const DeviceScene& sc, int mode, const float* ori
 void launch_bary_to_world(Ctx& cx, const float* verts, const int* faces, const float* bary, int64_t N, float* out);
 void launch_regulariser(Ctx& cx, int mode, const float* verts, int V, const int* faces, int F, const int* aff, double* grad, double* value);
 
+namespace ext {   // render_kernels_ext.cu: the launchers of the sample kernels built with the external-sample test hook
+void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* transient, uint32_t* vis, const double* wprefix);
+void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity);
+void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, int kind, const double* diff, const uint32_t* vis,
+                     const double* wprefix, const double* dprefix, double* out);
+}  // namespace ext
+
 }  // namespace nlos

@@ -278,3 +278,28 @@ def test_cuda_path_matches_reference_statistically(name, oracle):
         if draws[0][key] is None:
             continue
         check(name, key, fx['%s/%s/mean' % (name, key)], fx['%s/%s/std' % (name, key)], R, [x[key] for x in draws])
+
+
+GPU_SAME = sorted(name for name, c in SAME.items() if c['kind'] != 'vertex_gradient')    # the hook does not cover the per-bin vertex gradient
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', GPU_SAME)
+def test_cuda_path_matches_reference_on_the_reference_sample_stream(name, oracle):
+    """The CUDA path, through the reference-signature modules, on the reference's own (S,T) stream (test hook
+    nlos_ctx_set_external_samples): the same bars as the oracle's same-sample test — no transitivity through the oracle needed."""
+    fx = fixture(); c = SAME[name]
+    impl = GpuAdapter(oracle)
+    impl.ctx.set_external_samples(fx['same/stream'][:rc.stream_length(c)])
+    try:
+        got = rc.run_case(impl, oracle, c)
+    finally:
+        impl.ctx.set_external_samples(None)
+    for key, val in got.items():
+        if val is None:
+            continue                                                # first-generation gradient: the reference's index slips are not reproduced
+        want = fx['same/%s/%s' % (name, key)]
+        err = np.linalg.norm(val - want) / max(np.linalg.norm(want), 1e-300)
+        print('same(gpu)/%s/%s rel %.2e' % (name, key, err))
+        tol = 5e-4 if (key == 'T' and c.get('rs', 1) > 1 and c['kind'] == 'transient') else TOL_SAME[key]
+        assert np.linalg.norm(want) > 0 and err <= tol, (name, key, err)
