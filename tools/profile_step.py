@@ -11,6 +11,25 @@ wall = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 ctx = nb.Context(0)
 dev = torch.device('cuda', 0)
 o, n = scenes.wall_grid(wall); v, f = scenes.bunny()
+order = sys.argv[3] if len(sys.argv) > 3 else 'row'
+if order != 'row':        # experiment: feed the wall points in a spatially compact order (tiles / Morton) instead of row-major
+    iy, ix = np.divmod(np.arange(wall * wall), wall)
+    if order == 'random':
+        key = np.random.RandomState(0).permutation(wall * wall)
+    elif order == 'stride':
+        key = (np.arange(wall * wall) % 64) * 64 + np.arange(wall * wall) // 64      # chunk = one column = 64 points spread over y
+    elif order == 'scatter':
+        key = (ix % 8) * 512 + (iy % 8) * 64 + (iy // 8) * 8 + ix // 8                    # chunk = an 8x8 lattice spread over the whole wall
+    elif order == 'tile8':
+        key = ((iy // 8) * (wall // 8) + ix // 8) * 64 + (iy % 8) * 8 + ix % 8
+    else:
+        def spread(a):
+            r = np.zeros_like(a)
+            for b in range(8):
+                r |= ((a >> b) & 1) << (2 * b)
+            return r
+        key = spread(ix) | (spread(iy) << 1)
+    perm = np.argsort(key, kind='stable'); o = np.ascontiguousarray(o[perm]); n = np.ascontiguousarray(n[perm])
 L = o.shape[0]; B = 1200
 to = lambda a: torch.from_numpy(a).to(dev)
 d_o, d_n, d_v, d_f = to(o), to(n), to(v), to(f)
