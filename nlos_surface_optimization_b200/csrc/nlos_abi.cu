@@ -103,9 +103,17 @@ struct Job {
   int sr = 0, w_width = 0;   // first-generation API (stratified_transient_raytracer/): unclamped forward, box-filtered residual, one tap, '=' into gradient
 };
 
+// gradient kernel: sources per block (blockIdx.y).  The default (128) amortises the 9 atomics per (triangle, chunk); small meshes
+// get a smaller chunk so that the grid still fills the machine (F = 1125: 9 x 32 = 288 blocks on 148 SMs x 4 -> 9 x 133).
 int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
-  (void)cx; (void)key; (void)F;
+  (void)key;
   int c = dflt;
+  if (cx.chunk_gradient <= 0) {
+    const int64_t nx = ((int64_t)F + 127) / 128, target = 148 * 8;      // 128 = threads per block of k_gradient
+    const int64_t ny = (target + nx - 1) / nx;
+    const int64_t fit = std::max<int64_t>(8, L / std::max<int64_t>(ny, 1));
+    if (fit < c) c = (int)fit;
+  }
   if ((int64_t)c > L) c = (int)std::max<int64_t>(L, 1);
   // gridDim.y <= 65535
   while ((L + c - 1) / c > 65535) c *= 2;
