@@ -80,7 +80,10 @@ __device__ __forceinline__ bool draw_sample(const RenderParams& P, int64_t src_g
 //     the warp's visibility tile.
 // Back-facing / out-of-range samples therefore never occupy a lane during traversal, which is where the time goes.
 constexpr int kQCap = 64;        // ray queue capacity per warp (power of two, >= 63)
-constexpr int kTile = 256;       // sample slots per warp pass == visibility words in the warp tile
+#ifndef NLOS_TILE
+#define NLOS_TILE 256
+#endif
+constexpr int kTile = NLOS_TILE; // sample slots per warp pass (upper bound of the chunk_forward option) == visibility words in the warp tile
 #ifndef NLOS_REFILL
 #define NLOS_REFILL 24
 #endif

@@ -10,7 +10,7 @@ d_o, d_n, d_v, d_f = to(o), to(n), to(v), to(f)
 d_data = torch.zeros((L, B), dtype=torch.float64, device=dev); d_pl = torch.zeros(B, dtype=torch.float64, device=dev)
 d_w = torch.ones((L, B), dtype=torch.float64, device=dev); d_T = torch.zeros((L, B), dtype=torch.float64, device=dev); d_G = torch.zeros((v.shape[0], 3), dtype=torch.float64, device=dev)
 torch.cuda.synchronize(); ctx.set_option('timing', 1)
-for cf, cg in [(256, 128), (128, 128), (64, 128), (32, 128), (16, 128), (64, 64), (64, 256)]:
+for cf, cg in [(64, 128), (48, 128), (32, 128), (16, 128)]:
     ctx.set_option('chunk_forward', cf); ctx.set_option('chunk_gradient', cg)
     for i in range(3):
         renderer.renderStreamedGradient(d_o, d_n, d_v, d_f, 20000, 0.0, 1.44, 1.2e-3, d_T, d_pl, d_G, d_data, d_w, 10, 1, 1, 0, ctx=ctx); ctx.synchronize()
