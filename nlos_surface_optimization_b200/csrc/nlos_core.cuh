@@ -116,7 +116,10 @@ NLOS_HD int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)
 NLOS_HD int leaf_first(int ref) { return (~ref) >> 3; }
 NLOS_HD int leaf_count(int ref) { return ((~ref) & 7) + 1; }
 
-constexpr int kLeafMax = 4;      // a subtree with <= kLeafMax (<= 8) triangles is tested linearly
+#ifndef NLOS_LEAFMAX
+#define NLOS_LEAFMAX 4
+#endif
+constexpr int kLeafMax = NLOS_LEAFMAX;      // a subtree with <= kLeafMax (<= 8) triangles is tested linearly
 constexpr int kStack = 64;       // >= depth of a 62-bit-key LBVH
 
 NLOS_HD float safe_rcp(float x) {
