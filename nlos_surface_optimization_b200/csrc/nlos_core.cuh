@@ -426,6 +426,14 @@ NLOS_HD void tap_span(int64_t m0, int b, int r, int half /*2rs*/, int K, int& il
   ilo = lo < 0 ? 0 : (lo > K ? K : (int)lo);
   ihi = hi < 0 ? 0 : (hi > K ? K : (int)hi);
 }
+// 32-bit versions for the kernels (fine-bin indices are range-checked to +-2^30 first): the 64-bit ones above cost ~50 SASS
+// instructions per division (two per visible sample in the gradient kernel)
+NLOS_HD int floordiv32(int a, int b /* > 0 */) { const int q = a / b; return (a - q * b < 0) ? q - 1 : q; }
+NLOS_HD void tap_span32(int m0, int b, int r, int half /*2rs*/, int K, int& ilo, int& ihi) {
+  const int lo = b * r - m0 + half, hi = lo + r;
+  ilo = lo < 0 ? 0 : (lo > K ? K : lo);
+  ihi = hi < 0 ? 0 : (hi > K ? K : hi);
+}
 NLOS_HD int64_t floordiv(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
 }  // namespace nlos

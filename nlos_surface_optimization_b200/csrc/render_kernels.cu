@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
             // Gaussian smoothing + downsampling of TG.cpp:348-371 applied per sample: tap i of fine bin m lands in
             // coarse bin floor((m + i - 2rs)/r); the taps of one coarse bin are a contiguous run -> prefix sums
             const int half = 2 * P.r_fwd * P.s_bin;
-            int64_t b0 = floordiv((int64_t)bin - half, P.r_fwd), b1 = floordiv((int64_t)bin + half, P.r_fwd);
+            int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);      // bin < numBins * r_fwd < 2^31
             if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
-            for (int64_t b = b0; b <= b1; ++b) {
-              int ilo, ihi; tap_span(bin, (int)b, P.r_fwd, half, P.K, ilo, ihi);
+            for (int b = b0; b <= b1; ++b) {
+              int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
               if (ihi > ilo) atomicAdd(out + src * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
             }
           }
@@ -357,12 +357,13 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
       } else {
         // K-tap sums against the residual row, grouped per coarse bin (DESIGN.md "K-tap restructuring")
         const double x = ((double)(2.0f * hl) - (double)P.lb) * P.inv_res_fine;
-        const int64_t m0 = (int64_t)floor(x);
-        int64_t b0 = floordiv(m0 - half, P.r_grad), b1 = floordiv(m0 + half, P.r_grad);
+        if (!(x > -1.0e9 && x < 1.0e9)) continue;                     // no tap of such a sample lands in [0, numBins); keeps the rest in 32 bits
+        const int m0 = (int)floor(x);
+        int b0 = floordiv32(m0 - half, P.r_grad), b1 = floordiv32(m0 + half, P.r_grad);
         if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
         const double* drow = diff + s * P.numBins;
-        for (int64_t b = b0; b <= b1; ++b) {
-          int ilo, ihi; tap_span(m0, (int)b, P.r_grad, half, P.K, ilo, ihi);
+        for (int b = b0; b <= b1; ++b) {
+          int ilo, ihi; tap_span32(m0, b, P.r_grad, half, P.K, ilo, ihi);
           const double df = __ldg(drow + b);
           At += (s_w[ihi] - s_w[ilo]) * df;
           Bt += (s_d[ihi] - s_d[ilo]) * df;
