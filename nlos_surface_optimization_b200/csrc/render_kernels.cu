@@ -382,9 +382,9 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
         if (!GGX) {
           inten = alb * ff * ff;                                      // TG.cpp:950
           t1 = (2 * alb * c2 * c3) * (on * c3 - n * c2 + (4 * (-d)) * c2 * c3);   // :953
-          t1 = t1 / hl5;                                              // :954
+          t1 = t1 * (1.0f / hl5);                                     // :954 (Embree's Vec3fa / float is a reciprocal multiply too)
           if ((HAS_VN && P.testing_flag == 0) || P.sr) {              // :959-964; SR/SSG.cpp:266-271 always
-            gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn / hl4;
+            gn = ((-2 * alb) * d) * c3 * c2 * c2; gn = gn * (1.0f / hl4);
             const float ct = dot3(gn, n); gn = gn - n * ct;
           }
         } else {                                                      // ggx/TG.cpp:756-780
@@ -395,16 +395,16 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
           const f3 dx = -dw + d * dot3(d, dw) / hl;                   // :759 (sic)
           inten = alb * ff * ff * brdf;
           f3 t11 = (2 * c2 * c3) * (on * c3 - n * c2 + (4 * (-d)) * c2 * c3);
-          t11 = t11 / hl5; t11 = t11 * brdf;
+          t11 = t11 * (1.0f / hl5); t11 = t11 * brdf;
           t1 = t11 + (ff * ff) * dx;
           if (HAS_VN && P.testing_flag == 0) {
-            gn = (-2 * d) * c3 * c2 * c2 * brdf; gn = gn / hl4;
+            gn = (-2 * d) * c3 * c2 * c2 * brdf; gn = gn * (1.0f / hl4);
             gn = gn + (ff * ff) * dn;
             const float ct = dot3(gn, n); gn = gn - n * ct;
           }
         }
         f3 t2 = n * inten;                                            // :956
-        t2 = (t2 + gn) / (2 * t.st.A);                                // :966
+        t2 = (t2 + gn) * (1.0f / (2 * t.st.A));                       // :966
         // sum_i g_k(i) = (t1 b_k + t2 x e_k) At + grad_coef I d b_k Bt   (grad_coef = 2/sigma^2, or -2/res for the jitter kernel)
         const float fa = (float)At;
         const float fb = (float)((double)inten * P.grad_coef * Bt);
