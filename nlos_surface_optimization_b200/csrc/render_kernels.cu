@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         cur = occ ? kSentinel : stack[--sp];                     // occluded: drop the ray
       }
       if (cur == kDone) {                                        // traversal finished without an occluder: visible
-        const double dv = (double)val / (double)P.spp;           // TG.cpp:231-232
+        const double dv = P.spp == 1 ? (double)val : (double)val / (double)P.spp;   // TG.cpp:231-232 (x / 1.0 == x: skips an FP64 division)
         if (MODE == 1) atomicAdd(out + prim, dv);
         else if (bin >= 0) {
           if (!SMOOTH) atomicAdd(out + src * P.numBins + bin, dv);
@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
   // (32 independent L2 accesses in flight) and the words are then broadcast by shuffle, instead of one dependent L2 round trip
   // per slot at the top of the loop body.
   const int64_t slotA = s0 * P.spp, slotB = s1 * P.spp;
+  const double inv_spp = 1.0 / (double)P.spp;
   for (int64_t base = slotA; base < slotB; base += 32) {
     unsigned myword = 0u;
     if (USE_VIS) {
@@ -409,7 +410,6 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
         const float fa = (float)At;
         const float fb = (float)((double)inten * P.grad_coef * Bt);
         const float sA = t.st.A;
-        const double inv_spp = 1.0 / (double)P.spp;
         f3 gk;
         gk = (t1 * g.u + cross3(t2, e1)) * fa + d * (g.u * fb);
         g1x += (double)(sA * gk.x) * inv_spp; g1y += (double)(sA * gk.y) * inv_spp; g1z += (double)(sA * gk.z) * inv_spp;
