@@ -136,11 +136,32 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
     // per-lane traversal state of the ray in flight (cur == kSentinel: lane is idle)
     int cur = kSentinel, sp = 0, stack[kStack];
     Ray ray; float ts = 0.f, val = 0.f; int bin = -1, prim = 0, tri_lane = 0, slot_local = 0; int64_t src = 0;
+    bool pending = false;                                        // this lane's last ray ended visible and its contribution is not added yet
     ray.o = ray.d = ray.id = ray.oid = mk3(0.f, 0.f, 0.f);
     for (;;) {
       const unsigned idle_mask = __ballot_sync(0xffffffffu, cur == kSentinel);
       const int n_idle = __popc(idle_mask);
       if (n_idle >= kRefill) {
+        if (pending) {                                             // rays that ended visible since the last refill
+          const double dv = P.spp == 1 ? (double)val : (double)val / (double)P.spp;   // TG.cpp:231-232 (x / 1.0 == x: skips an FP64 division)
+          if (MODE == 1) atomicAdd(out + prim, dv);
+          else if (bin >= 0) {
+            if (!SMOOTH) atomicAdd(out + src * P.numBins + bin, dv);
+            else {
+              // Gaussian smoothing + downsampling of TG.cpp:348-371 applied per sample: tap i of fine bin m lands in
+              // coarse bin floor((m + i - 2rs)/r); the taps of one coarse bin are a contiguous run -> prefix sums
+              const int half = 2 * P.r_fwd * P.s_bin;
+              int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);      // bin < numBins * r_fwd < 2^31
+              if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+              for (int b = b0; b <= b1; ++b) {
+                int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
+                if (ihi > ilo) atomicAdd(out + src * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
+              }
+            }
+          }
+          if (WRITE_VIS) atomicOr(&ws.tile[slot_local], 1u << tri_lane);
+          pending = false;
+        }
         // ---------------- phase A: generate + compact until the idle lanes can be fed
         while (qcount < n_idle && gen < nslots) {
           const int64_t slot = slot0 + gen;
@@ -244,26 +265,9 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
         for (int j = 0; j < cnt && !occ; ++j) occ = tri_occludes_fast(sc.ttris, first + j, ray, ts, prim);
         cur = occ ? kSentinel : stack[--sp];                     // occluded: drop the ray
       }
-      if (cur == kDone) {                                        // traversal finished without an occluder: visible
-        const double dv = P.spp == 1 ? (double)val : (double)val / (double)P.spp;   // TG.cpp:231-232 (x / 1.0 == x: skips an FP64 division)
-        if (MODE == 1) atomicAdd(out + prim, dv);
-        else if (bin >= 0) {
-          if (!SMOOTH) atomicAdd(out + src * P.numBins + bin, dv);
-          else {
-            // Gaussian smoothing + downsampling of TG.cpp:348-371 applied per sample: tap i of fine bin m lands in
-            // coarse bin floor((m + i - 2rs)/r); the taps of one coarse bin are a contiguous run -> prefix sums
-            const int half = 2 * P.r_fwd * P.s_bin;
-            int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);      // bin < numBins * r_fwd < 2^31
-            if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
-            for (int b = b0; b <= b1; ++b) {
-              int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
-              if (ihi > ilo) atomicAdd(out + src * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
-            }
-          }
-        }
-        if (WRITE_VIS) atomicOr(&ws.tile[slot_local], 1u << tri_lane);
-        cur = kSentinel;
-      }
+      // a ray that ended visible only raises a flag: its histogram update runs at the next refill, when >= kRefill lanes are idle and
+      // most of them have one pending, instead of at 10-14 active lanes right here (forward 24.4 -> 23.8 ms, smoothed forward 28.0 -> 25.1)
+      if (cur == kDone) { pending = true; cur = kSentinel; }
     }
     if (WRITE_VIS) {
       __syncwarp();
