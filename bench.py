@@ -350,7 +350,7 @@ def run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'fp32', 'kernel': 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                         'traffic': 31.3e6,     # bytes: dram__bytes_read.sum + dram__bytes_write.sum of one k_forward launch, ncu --set full (profiles/r1_ncu_full_summary.txt)
+                         'traffic': 30.4e6,     # bytes: dram__bytes_read.sum + dram__bytes_write.sum of one k_forward launch, ncu --set full (profiles/r1_ncu_full_summary.txt)
                          'traffic_unit': 'bytes of DRAM per k_forward launch (ncu); the unit of achieved/peak is TFLOP/s',
                          'peak_source': peak_how, 'flops_per_path_sample': flops_fwd_sample, 'canonical_box_tests_per_ray': box, 'canonical_tri_tests_per_ray': tri,
                          'kernel_ms': fwd_ms,
