@@ -10,8 +10,11 @@
 //   * visibility is an ANY-HIT query bounded by the self-hit distance (equivalent to the reference's
 //     "nearest hit == sampled triangle", TG.cpp:206) and is skipped for samples whose contribution is
 //     exactly zero (back-facing / out of range)
-//   * the forward pass leaves one visibility bit per sample (warp ballot) that the gradient pass reuses,
-//     so the gradient pass traces no rays (legitimate: both passes use identical samples)
+//   * the forward pass leaves one visibility bit per sample (shared-memory tile per warp) that the gradient pass
+//     reuses, so the gradient pass traces no rays (legitimate: both passes use identical samples)
+//   * forward kernel: the four warps of a block own the SAME triangle tile and take different slot chunks (L1 locality);
+//     generated samples are compacted into a per-warp ray queue and lanes are refilled from it while others still traverse;
+//     histogram updates of finished rays are batched at the refills (see k_forward)
 //
 // Reference: smoothed_transient/transient_and_gradient.cpp:122-237 (forward task), :843-1007 (gradient task),
 // :571-695 (albedo), :22-119 (intensity); ggx/transient_and_gradient.cpp:126-243, 385-512, 648-823.
@@ -29,7 +32,7 @@ constexpr int kBlock = 128;
 #ifndef NLOS_FWD_BLOCK
 #define NLOS_FWD_BLOCK 128
 #endif
-constexpr int kFwdBlock = NLOS_FWD_BLOCK;   // threads per block of the forward kernel (one warp = one triangle tile)
+constexpr int kFwdBlock = NLOS_FWD_BLOCK;   // threads per block of the forward kernel (all its warps share one triangle tile)
 
 struct TriRegs {
   ShadeTri st; TriRec tr; int prim;
