@@ -27,7 +27,7 @@ __device__ __forceinline__ f3 ldv(const float* __restrict__ v, int i) { return m
 
 __global__ void k_init_bounds(SceneBounds* sb) {
   if (threadIdx.x == 0) {
-    for (int a = 0; a < 3; ++a) { sb->lo[a] = f2ord(3.0e38f); sb->hi[a] = f2ord(-3.0e38f); }
+    for (int a = 0; a < 3; ++a) { sb->lo[a] = sb->vlo[a] = f2ord(3.0e38f); sb->hi[a] = sb->vhi[a] = f2ord(-3.0e38f); }
     sb->absmax = 0u; sb->pad_ = 0u;
   }
 }
@@ -43,21 +43,28 @@ __global__ void k_absmax(const float* __restrict__ a, size_t n, SceneBounds* sb)
 __global__ void k_scene_bounds(const float* __restrict__ verts, const int* __restrict__ faces, int F, SceneBounds* sb) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  float vl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, vh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};     // bounds of the vertices the faces use
   if (f < F) {
     const f3 a = ldv(verts, faces[3 * (size_t)f]), b = ldv(verts, faces[3 * (size_t)f + 1]), c = ldv(verts, faces[3 * (size_t)f + 2]);
-    const float cx = 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x)));
-    const float cy = 0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y)));
-    const float cz = 0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z)));
+    vl[0] = fminf(a.x, fminf(b.x, c.x)); vh[0] = fmaxf(a.x, fmaxf(b.x, c.x));
+    vl[1] = fminf(a.y, fminf(b.y, c.y)); vh[1] = fmaxf(a.y, fmaxf(b.y, c.y));
+    vl[2] = fminf(a.z, fminf(b.z, c.z)); vh[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+    const float cx = 0.5f * (vl[0] + vh[0]);
+    const float cy = 0.5f * (vl[1] + vh[1]);
+    const float cz = 0.5f * (vl[2] + vh[2]);
     lo[0] = hi[0] = cx; lo[1] = hi[1] = cy; lo[2] = hi[2] = cz;
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+    for (int o = 16; o; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      vl[k] = fminf(vl[k], __shfl_xor_sync(0xffffffffu, vl[k], o)); vh[k] = fmaxf(vh[k], __shfl_xor_sync(0xffffffffu, vh[k], o));
+    }
   }
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMin(&sb->lo[k], f2ord(lo[k])); atomicMax(&sb->hi[k], f2ord(hi[k])); }
+    for (int k = 0; k < 3; ++k) { atomicMin(&sb->lo[k], f2ord(lo[k])); atomicMax(&sb->hi[k], f2ord(hi[k])); atomicMin(&sb->vlo[k], f2ord(vl[k])); atomicMax(&sb->vhi[k], f2ord(vh[k])); }
   }
 }
 
@@ -209,7 +216,7 @@ void build_scene(Ctx& cx, const float* d_verts, int V, const int* d_faces, int F
     cx.launches += 3;
   }
   NLOS_CUDA_OK(cudaGetLastError());
-  out.ttris = ttris; out.stris = stris; out.nodes = nodes;
+  out.ttris = ttris; out.stris = stris; out.nodes = nodes; out.bounds = sb; out.verts = d_verts;
   out.root_count = F <= kLeafMax ? F : 0;
 }
 

@@ -348,6 +348,7 @@ int nlos_ctx_create(int device, nlos_ctx** out) {
   nlos_ctx* c = new (std::nothrow) nlos_ctx();
   if (!c) return NLOS_ERR_NOMEM;
   c->cx.device = device;
+  c->cx.num_sms = prop.multiProcessorCount;
   try {
     NLOS_CUDA_OK(cudaSetDevice(device));
     NLOS_CUDA_OK(cudaStreamCreateWithFlags(&c->cx.stream, cudaStreamNonBlocking));
@@ -400,6 +401,8 @@ int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value) {
   else if (k == "chunk_forward") ctx->cx.chunk_forward = (int)value;
   else if (k == "chunk_gradient") ctx->cx.chunk_gradient = (int)value;
   else if (k == "timing") ctx->cx.timing_enabled = value != 0;
+  else if (k == "forward_algo") { if (value < 0 || value > 2) { ctx->cx.last_error = "forward_algo must be 0 (auto), 1 (bvh) or 2 (grid)"; return NLOS_ERR_INVALID; } ctx->cx.forward_algo = (int)value; }
+  else if (k == "grid_res") { if (value < 0 || value > 4096) { ctx->cx.last_error = "grid_res out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_res = (int)value; }
   else { ctx->cx.last_error = "unknown option " + k; return NLOS_ERR_INVALID; }
   return NLOS_OK;
 }

@@ -176,15 +176,15 @@ NLOS_HD bool tri_occludes(const float4* __restrict__ ttris, int j, const Ray& r,
 // Same predicate as tri_occludes() with one combined validity test and the IEEE division only when the outcome is not already
 // decided by a 4-ulp bracket around T = t_self * |den| (the division result is what the contract compares, so the
 // undecided sliver still divides; logic only, no arithmetic of isect() is changed).
-NLOS_HD bool tri_occludes_fast(const float4* __restrict__ ttris, int j, const Ray& r, float t_self, int prim_self) {
+NLOS_HD bool tri_occludes_od(const float4* __restrict__ ttris, int j, f3 ro, f3 rd, float t_self, int prim_self) {
   float4 q0, q1, q2, q3;
   ld256(ttris + 4 * (size_t)j, q0, q1);
   ld256(ttris + 4 * (size_t)j + 2, q2, q3);
   const int prim = f2i(q0.w);
-  const f3 C = xyz(q0) - r.o;
-  const f3 R = cross3(C, r.d);
+  const f3 C = xyz(q0) - ro;
+  const f3 R = cross3(C, rd);
   const f3 Ng = xyz(q3);
-  const float den = dot3(Ng, r.d);
+  const float den = dot3(Ng, rd);
   const float absDen = fabsf(den);
   const float sgn = den < 0.0f ? -1.0f : 1.0f;
   const float U = dot3(R, xyz(q2)) * sgn;
@@ -197,6 +197,9 @@ NLOS_HD bool tri_occludes_fast(const float4* __restrict__ ttris, int j, const Ra
   if (T > ref * 1.00000048f) return false;         // certainly > t_self
   const float t = T / absDen;
   return t < t_self || (t == t_self && prim < prim_self);
+}
+NLOS_HD bool tri_occludes_fast(const float4* __restrict__ ttris, int j, const Ray& r, float t_self, int prim_self) {
+  return tri_occludes_od(ttris, j, r.o, r.d, t_self, prim_self);
 }
 
 // Any-hit query equivalent to "nearest hit (min t, ties -> lowest prim) is NOT prim_self".
@@ -300,6 +303,108 @@ NLOS_HD bool occluded_ww(const BvhNode* __restrict__ nodes, const float4* __rest
   }
   return false;
 }
+
+// ------------------------------------------------------------------ per-source perspective grid (forward pass, DESIGN.md "K1g")
+// Every ray of one wall point o leaves the same origin, and (outside the first-generation mode) a traced ray has n_o.d > 0, so
+// seen from o the scene is a 2-D picture:  u = (x-o).a / (x-o).n,  v = (x-o).b / (x-o).n  with (a, b, n) an orthonormal frame
+// around the wall normal.  A ray is ONE point of that picture; a triangle can only be hit by rays whose point lies inside its
+// projected bounding rectangle (padded for float round-off).  The rectangles are binned into a G x G grid per source; a ray
+// scans the list of its cell with a packed integer pre-check and runs the exact Moeller-Trumbore test (tri_occludes_fast) on
+// the survivors — the visibility ANSWER is still the brute-force definition, the grid only decides which triangles are tried.
+//
+// Coordinates are quantised to Q = G * 128 steps per axis (7 sub-cell bits).  An entry holds the triangle's rectangle clipped to
+// the cell, in sub-cell units, as four guarded bytes  E = [0x80-lo_u | 0x80+hi_u | 0x80-lo_v | 0x80+hi_v];  the ray holds
+// R = su - (su<<8) + (sv<<16) - (sv<<24) (mod 2^32).  Every byte lane of E + R stays within [1,255] (no carry between lanes), and
+// bit 7 of the four lanes says su >= lo_u, su <= hi_u, sv >= lo_v, sv <= hi_v: the whole 2-D containment test is one add, one
+// and, one compare.
+struct PGridFrame {
+  f3 o, a, b, n;            // origin, projection frame (n = unit wall normal)
+  float u0, v0, su, sv;     // uq = clamp(floor((u - u0) * su), 0, Q-1)
+  int G;                    // cells per axis (0: no grid for this source -> per-ray BVH query)
+  float qmax;               // Q - 1 as float
+};
+constexpr int kPgSub = 7;                      // sub-cell bits
+constexpr unsigned kPgMask = 0x80808080u;
+constexpr float kPgPad = 1.0e-5f;              // relative padding of projected coordinates (~30x the float error of the projection)
+
+NLOS_HD float pg_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+NLOS_HD void pg_make_axes(f3 n_raw, f3& a, f3& b, f3& n, bool& ok) {
+  const float l = len3(n_raw);
+  ok = l > 0.0f && l < 3.0e38f;
+  n = ok ? n_raw * pg_rcp(l) : mk3(0.f, 0.f, 1.f);
+  const float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
+  f3 e = (ax <= ay && ax <= az) ? mk3(1.f, 0.f, 0.f) : (ay <= az ? mk3(0.f, 1.f, 0.f) : mk3(0.f, 0.f, 1.f));
+  const float k = dot3(e, n);
+  a = e - n * k; a = a * pg_rcp(len3(a));
+  b = cross3(n, a);
+}
+// projection of a scene point: picture coordinates (u,v), depth z along n (grid mode needs z >= zmin > 0 for every vertex) and
+// m = relative round-off margin of this projection (the padding of a coordinate c is m * (1 + |c|))
+NLOS_HD void pg_project(const PGridFrame& g, f3 x, float& u, float& v, float& m, float& z) {
+  const f3 rel = x - g.o;
+  z = dot3(rel, g.n);
+  const float rz = pg_rcp(z);
+  u = dot3(rel, g.a) * rz; v = dot3(rel, g.b) * rz;
+  m = kPgPad * ((fabsf(rel.x) + fabsf(rel.y) + fabsf(rel.z)) * rz);
+}
+NLOS_HD int pg_quant(float x, float x0, float s, float qmax) {   // monotone in x
+  float t = (x - x0) * s;
+  t = fminf(fmaxf(t, 0.0f), qmax);
+  return (int)t;
+}
+// quantised rectangle [a0,a1] x [b0,b1] of a triangle from the picture coordinates of its vertices and the source-wide padding
+// (pad_u, pad_v >= the padding of every single vertex)
+NLOS_HD void pg_tri_rect(const PGridFrame& g, float u1, float v1, float u2, float v2, float u3, float v3, float pad_u, float pad_v,
+                         int& a0, int& a1, int& b0, int& b1) {
+  const float ulo = fminf(u1, fminf(u2, u3)) - pad_u, uhi = fmaxf(u1, fmaxf(u2, u3)) + pad_u;
+  const float vlo = fminf(v1, fminf(v2, v3)) - pad_v, vhi = fmaxf(v1, fmaxf(v2, v3)) + pad_v;
+  a0 = pg_quant(ulo, g.u0, g.su, g.qmax); a1 = pg_quant(uhi, g.u0, g.su, g.qmax);
+  b0 = pg_quant(vlo, g.v0, g.sv, g.qmax); b1 = pg_quant(vhi, g.v0, g.sv, g.qmax);
+}
+// entry word of a rectangle clipped to cell (cx, cy)
+NLOS_HD unsigned pg_entry(int uq0, int uq1, int vq0, int vq1, int cx, int cy) {
+  const int bu = cx << kPgSub, bv = cy << kPgSub;
+  int lu = uq0 - bu, hu = uq1 - bu, lv = vq0 - bv, hv = vq1 - bv;
+  lu = lu < 0 ? 0 : lu; hu = hu > 127 ? 127 : hu; lv = lv < 0 ? 0 : lv; hv = hv > 127 ? 127 : hv;
+  return (unsigned)(0x80 - lu) | ((unsigned)(0x80 + hu) << 8) | ((unsigned)(0x80 - lv) << 16) | ((unsigned)(0x80 + hv) << 24);
+}
+// quantised picture point of a ray direction d (n.d > 0): its cell (cx, cy) and its pre-check word
+NLOS_HD void pg_ray(const PGridFrame& g, f3 d, int& cx, int& cy, unsigned& R) {
+  const float rz = pg_rcp(dot3(d, g.n));
+  const int uq = pg_quant(dot3(d, g.a) * rz, g.u0, g.su, g.qmax), vq = pg_quant(dot3(d, g.b) * rz, g.v0, g.sv, g.qmax);
+  cx = uq >> kPgSub; cy = vq >> kPgSub;
+  const unsigned su = (unsigned)(uq & 127), sv = (unsigned)(vq & 127);
+  R = su - (su << 8) + (sv << 16) - (sv << 24);
+}
+NLOS_HD bool pg_precheck(unsigned E, unsigned R) { return ((E + R) & kPgMask) == kPgMask; }
+// frame of one source: axes only (G = 0: no grid yet); pg_set_rect() then fixes the quantisation from the picture rectangle
+// [U0,U1] x [V0,V1] that contains every projected vertex (with its padding)
+NLOS_HD void pg_init_frame(f3 o, f3 n_raw, PGridFrame& g, bool& ok) {
+  pg_make_axes(n_raw, g.a, g.b, g.n, ok);
+  g.o = o; g.G = 0; g.u0 = g.v0 = 0.f; g.su = g.sv = 1.f; g.qmax = 0.f;
+}
+NLOS_HD void pg_set_rect(PGridFrame& g, float U0, float U1, float V0, float V1, int G) {
+  g.G = 0;
+  if (G <= 0 || !(U1 >= U0) || !(V1 >= V0)) return;
+  const float eu = 1.0e-3f * (U1 - U0) + 1.0e-6f, ev = 1.0e-3f * (V1 - V0) + 1.0e-6f;
+  U0 -= eu; U1 += eu; V0 -= ev; V1 += ev;
+  if (!(U1 - U0 < 3.0e30f) || !(V1 - V0 < 3.0e30f)) return;
+  const float Q = (float)(G << kPgSub);
+  g.u0 = U0; g.v0 = V0; g.su = Q / (U1 - U0); g.sv = Q / (V1 - V0); g.qmax = Q - 1.0f; g.G = G;
+}
+// halve the resolution (entry budget exceeded): same rectangle, coarser cells
+NLOS_HD void pg_coarsen(PGridFrame& g) {
+  const int G = g.G > 1 ? g.G >> 1 : 1;
+  const float k = (float)G / (float)g.G;
+  g.su *= k; g.sv *= k; g.G = G; g.qmax = (float)(G << kPgSub) - 1.0f;
+}
+NLOS_HD float pg_zmin(const float* blo, const float* bhi) { return 1.0e-3f * ((bhi[0] - blo[0]) + (bhi[1] - blo[1]) + (bhi[2] - blo[2])) + 1.0e-30f; }
 
 // ------------------------------------------------------------------ LBVH construction helpers (Karras 2012)
 NLOS_HD uint32_t expand_bits10(uint32_t v) {

@@ -47,6 +47,9 @@ struct Ctx {
   int timing_enabled = 0;
   int chunk_forward = 0;         // sources per blockIdx.y in the forward pass (0 = auto)
   int chunk_gradient = 0;        // same for the gradient pass
+  int forward_algo = 0;          // 0 auto (perspective grid where it applies), 1 BVH traversal kernel, 2 perspective grid
+  int grid_res = 0;              // cells per axis of the perspective grid (0 = auto from the triangle count)
+  int num_sms = 0;               // multiprocessors of the device (filled at context creation)
   Timing timing;
   uint64_t launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
   std::map<std::string, DevBuf> bufs;

@@ -8,6 +8,8 @@
 
 namespace nlos {
 
+struct SceneBounds { unsigned lo[3], hi[3]; unsigned absmax; unsigned pad_; unsigned vlo[3], vhi[3]; };   // centroid bounds, max |coordinate|, vertex bounds (ordered-uint floats)
+
 // Mesh + acceleration structure resident in HBM for the duration of one call (rebuilt per call like the
 // reference rebuilds its Embree scene, SSG.cpp:473-511).  All per-triangle arrays are in Morton order.
 struct DeviceScene {
@@ -18,9 +20,10 @@ struct DeviceScene {
   const BvhNode* nodes = nullptr;  // [max(F-1,1)]
   const float* vnormal = nullptr;  // [V,3] or null (caller order)
   const float* valbedo = nullptr;  // [V]   or null
+  const float* verts = nullptr;    // [V,3] caller order
+  const SceneBounds* bounds = nullptr;   // device copy of the scene bounds (perspective-grid forward kernel)
 };
 
-struct SceneBounds { unsigned lo[3], hi[3]; unsigned absmax; unsigned pad_; };
 
 // ordered-uint encoding so that atomicMin/atomicMax work on floats of either sign
 __device__ __forceinline__ unsigned f2ord(float f) { unsigned u = (unsigned)__float_as_int(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }

@@ -18,6 +18,8 @@
 //
 // Reference: smoothed_transient/transient_and_gradient.cpp:122-237 (forward task), :843-1007 (gradient task),
 // :571-695 (albedo), :22-119 (intensity); ggx/transient_and_gradient.cpp:126-243, 385-512, 648-823.
+#include <algorithm>
+#include <cmath>
 #include "nlos_ctx.h"
 #include "render_kernels.h"
 
@@ -280,6 +282,333 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------- K1g forward, perspective grid
+// One BLOCK per wall point (persistent blocks stride over the sources).  Seen from the wall point the scene is a 2-D picture
+// (nlos_core.cuh "per-source perspective grid"); per source the block
+//   pass 0  projects the VERTICES once (picture coordinates to a per-block scratch array, picture rectangle, round-off padding,
+//           "everything safely in front" check)
+//   pass 1  per triangle: quantised rectangle from its three projected vertices (kept for pass 2); counts, per grid cell
+//           (shared memory), the triangles whose rectangle overlaps it;  block scan -> offsets
+//           (entry budget exceeded -> halve the resolution and recount: no host round trip, the answer does not depend on G)
+//   pass 2  writes the cell lists into this block's slice of a global scratch buffer: 4-byte entry words (the rectangle clipped
+//           to the cell, four guarded bytes) and, in a parallel array, the triangle index
+//   pass 3  lane <-> triangle as in k_forward: draw the sample, self intersection, shading.  The samples of a warp that can
+//           contribute fall into a few neighbouring cells; the warp copies the entry words of that cell window into shared
+//           memory (coalesced, all loads in flight at once), every lane scans the list of ITS cell there with the packed
+//           pre-check (one add, one and, one compare per entry) and queues the survivors; the queued triangles then get the
+//           exact test tri_occludes_od with all lanes of the warp in the same loop.  No tree walk, no per-lane stack.
+// Visibility is still "no other triangle beats (t_self, prim)" over the exact float test — the grid only selects candidates,
+// conservatively (tests/emul/pgrid_emul.cpp checks the selection against the BVH query on every ray of C-bunny).
+// A source that does not see the whole mesh safely in front of it (a vertex with depth < zmin along the wall normal) falls
+// back to the per-ray BVH query inside this kernel.
+#ifndef NLOS_GRID_BLOCK
+#define NLOS_GRID_BLOCK 1024
+#endif
+#ifndef NLOS_GRID_MINBLOCKS
+#define NLOS_GRID_MINBLOCKS 1
+#endif
+constexpr int kGridBlock = NLOS_GRID_BLOCK;
+#ifndef NLOS_GRID_K
+#define NLOS_GRID_K 4
+#endif
+static_assert(NLOS_GRID_K == 1 || NLOS_GRID_K == 2 || NLOS_GRID_K == 4, "the slice index is packed into 2 bits");
+constexpr int kGridK = NLOS_GRID_K;           // depth slices per picture cell (1, 2 or 4): a ray only scans the slices up to its own depth
+constexpr int kGridPush = 8;               // candidates a lane hands to the warp's work pool per round
+constexpr int kGridPool = 32 * kGridPush;  // (ray, candidate) work items per round
+struct GridWarp {                          // per-warp scratch of pass 3
+  float dx[32], dy[32], dz[32], ts[32]; int prim[32];   // the warp's rays, readable by every lane
+  unsigned pool[kGridPool];                // work items: ray lane << 27 | entry position
+  unsigned occ;                            // bit l: the ray of lane l is occluded
+  unsigned pad_[3];
+};
+struct GridShared {
+  PGridFrame fr;
+  float zmin, pad_u, pad_v;
+  float z0, sz, pad_z;                     // depth slice of depth z: clamp(floor((z - z0) * sz), 0, kGridK-1)
+  int use_grid;
+  unsigned rect[6];                        // ordered-uint min u, max u, min v, max v, min z, max z of the projected vertices
+  unsigned maxm;                           // max round-off margin (float bits, m >= 0)
+  unsigned wsum[kGridBlock / 32];
+};
+struct GridScratch { float4* proj; uint2* rect; unsigned* entE; unsigned* entI; };
+
+// exclusive prefix sum of the counts a[0..n), each rounded up to a multiple of 4, in place (shared memory); returns the total;
+// per-thread runs of odd length avoid bank conflicts
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned* a, int n, unsigned* wsum) {
+  const int T = kGridBlock, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = ((n + T - 1) / T) | 1;
+  const int b = min(n, tid * per), e = min(n, b + per);
+  unsigned sum = 0;
+  for (int i = b; i < e; ++i) sum += (a[i] + 3u) & ~3u;               // every list is padded to whole groups of 4 entries
+  unsigned x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < T / 32 ? wsum[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    if (lane < T / 32) wsum[lane] = w;
+  }
+  __syncthreads();
+  unsigned base = (warp ? wsum[warp - 1] : 0u) + x - sum;
+  const unsigned total = wsum[T / 32 - 1];
+  for (int i = b; i < e; ++i) { const unsigned c = (a[i] + 3u) & ~3u; a[i] = base; base += c; }
+  return total;
+}
+
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
+__global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_grid(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
+                                                    uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
+                                                    const GridScratch scr, unsigned cap, int G0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GridShared& gs = *reinterpret_cast<GridShared*>(smem_raw);
+  double* s_w = reinterpret_cast<double*>(smem_raw + ((sizeof(GridShared) + 15) & ~size_t(15)));                  // SMOOTH: tap prefix sums
+  GridWarp* gw_all = reinterpret_cast<GridWarp*>(reinterpret_cast<unsigned char*>(s_w) + (SMOOTH ? (((size_t)(P.K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0));
+  unsigned* cells = reinterpret_cast<unsigned*>(gw_all + kGridBlock / 32);
+  if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += kGridBlock) s_w[i] = wprefix[i]; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  GridWarp& gw = gw_all[warp];
+  float4* __restrict__ proj = scr.proj + (size_t)blockIdx.x * sc.V;
+  uint2* __restrict__ trect = scr.rect + (size_t)blockIdx.x * sc.F;
+  unsigned* __restrict__ entE = scr.entE + (size_t)blockIdx.x * cap;
+  unsigned* __restrict__ entI = scr.entI + (size_t)blockIdx.x * cap;
+  const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
+  const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
+  const int F = sc.F;
+  const float pad = __int_as_float((int)sc.bounds->absmax) * (1.0f / 65536.0f);
+  for (int64_t s = blockIdx.x; s < P.L; s += gridDim.x) {
+    const f3 o = xyz(__ldg(P.origin + s)), on = xyz(__ldg(P.onormal + s));
+    // ---------------- frame
+    if (tid == 0) {
+      bool ok; pg_init_frame(o, on, gs.fr, ok);
+      float blo[3], bhi[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { blo[k] = ord2f(sc.bounds->vlo[k]) - pad; bhi[k] = ord2f(sc.bounds->vhi[k]) + pad; }
+      gs.zmin = pg_zmin(blo, bhi);
+      gs.use_grid = (ok && G0 > 0) ? 1 : 0;
+      gs.rect[0] = f2ord(3.0e38f); gs.rect[1] = f2ord(-3.0e38f); gs.rect[2] = f2ord(3.0e38f); gs.rect[3] = f2ord(-3.0e38f); gs.rect[4] = f2ord(3.0e38f); gs.rect[5] = f2ord(-3.0e38f); gs.maxm = 0u;
+    }
+    __syncthreads();
+    // ---------------- pass 0: project the vertices
+    if (gs.use_grid) {
+      const PGridFrame fr = gs.fr; const float zmin = gs.zmin;
+      float U0 = 3.0e38f, U1 = -3.0e38f, V0 = 3.0e38f, V1 = -3.0e38f, Z0 = 3.0e38f, Z1 = -3.0e38f, mm = 0.f; bool zok = true;
+      for (int i = tid; i < sc.V; i += kGridBlock) {
+        const f3 x = mk3(__ldg(sc.verts + 3 * (size_t)i), __ldg(sc.verts + 3 * (size_t)i + 1), __ldg(sc.verts + 3 * (size_t)i + 2));
+        float u, v, m, z; pg_project(fr, x, u, v, m, z);
+        zok = zok && (z >= zmin);
+        proj[i] = make_float4(u, v, z, 0.f);
+        U0 = fminf(U0, u); U1 = fmaxf(U1, u); V0 = fminf(V0, v); V1 = fmaxf(V1, v); Z0 = fminf(Z0, z); Z1 = fmaxf(Z1, z); mm = fmaxf(mm, m);
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        U0 = fminf(U0, __shfl_xor_sync(0xffffffffu, U0, d)); U1 = fmaxf(U1, __shfl_xor_sync(0xffffffffu, U1, d));
+        V0 = fminf(V0, __shfl_xor_sync(0xffffffffu, V0, d)); V1 = fmaxf(V1, __shfl_xor_sync(0xffffffffu, V1, d));
+        Z0 = fminf(Z0, __shfl_xor_sync(0xffffffffu, Z0, d)); Z1 = fmaxf(Z1, __shfl_xor_sync(0xffffffffu, Z1, d));
+        mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, d));
+      }
+      zok = __all_sync(0xffffffffu, zok);
+      if (lane == 0) {
+        if (!zok || !(mm < 1.0f)) gs.use_grid = 0;
+        atomicMin(&gs.rect[0], f2ord(U0)); atomicMax(&gs.rect[1], f2ord(U1)); atomicMin(&gs.rect[2], f2ord(V0)); atomicMax(&gs.rect[3], f2ord(V1));
+        atomicMin(&gs.rect[4], f2ord(Z0)); atomicMax(&gs.rect[5], f2ord(Z1));
+        atomicMax(&gs.maxm, (unsigned)__float_as_int(mm));
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && gs.use_grid) {
+      float U0 = ord2f(gs.rect[0]), U1 = ord2f(gs.rect[1]), V0 = ord2f(gs.rect[2]), V1 = ord2f(gs.rect[3]);
+      const float mm = __int_as_float((int)gs.maxm);
+      gs.pad_u = mm * (1.0f + fmaxf(fabsf(U0), fabsf(U1))); gs.pad_v = mm * (1.0f + fmaxf(fabsf(V0), fabsf(V1)));
+      pg_set_rect(gs.fr, U0 - gs.pad_u, U1 + gs.pad_u, V0 - gs.pad_v, V1 + gs.pad_v, G0);
+      const float Z0 = ord2f(gs.rect[4]), Z1 = ord2f(gs.rect[5]);
+      gs.pad_z = 1.0e-5f * fabsf(Z1); gs.z0 = Z0; gs.sz = (float)kGridK / fmaxf(Z1 - Z0, 1.0e-30f);
+      if (gs.fr.G == 0) gs.use_grid = 0;
+    }
+    __syncthreads();
+    // ---------------- pass 1: count (coarsen until the entries fit), then pass 2: fill
+    while (gs.use_grid) {
+      const PGridFrame fr = gs.fr; const float pad_u = gs.pad_u, pad_v = gs.pad_v, z0 = gs.z0, sz = gs.sz, pad_z = gs.pad_z;
+      const int G = fr.G, ncell = G * G * kGridK;
+      for (int i = tid; i < ncell; i += kGridBlock) cells[i] = 0u;
+      __syncthreads();
+      for (int p = tid; p < F; p += kGridBlock) {
+        const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+        const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
+        int a0, a1, b0, b1;
+        pg_tri_rect(fr, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, pad_u, pad_v, a0, a1, b0, b1);
+        // depth slice of the triangle's nearest vertex: it can only occlude rays whose own hit is at least that deep
+        const int kz = pg_quant(fminf(p1.z, fminf(p2.z, p3.z)) - pad_z, z0, sz, (float)(kGridK - 1));
+        trect[p] = make_uint2((unsigned)a0 | ((unsigned)a1 << 16) | ((unsigned)(kz & 1) << 15) | ((unsigned)(kz >> 1) << 31), (unsigned)b0 | ((unsigned)b1 << 16));
+        const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
+        const int cy0 = b0 >> kPgSub;
+        if (cx0 == cx1 && cy0 == cy1) atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);       // the common case: one cell
+        else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+      }
+      __syncthreads();
+      const unsigned total = block_exclusive_scan(cells, ncell, gs.wsum);
+      __syncthreads();
+      if (total <= cap) {
+        for (int p = tid; p < F; p += kGridBlock) {
+          const uint2 r = trect[p];
+          const int a0 = (int)(r.x & 0x7fffu), a1 = (int)((r.x >> 16) & 0x7fffu), b0 = (int)(r.y & 0xffffu), b1 = (int)(r.y >> 16);
+          const int kz = (int)((r.x >> 15) & 1u) | (int)((r.x >> 31) << 1);
+          const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
+          const int cy0 = b0 >> kPgSub;
+          if (cx0 == cx1 && cy0 == cy1) {                                                      // the common case: one cell
+            const unsigned pos = atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);
+            entE[pos] = pg_entry(a0, a1, b0, b1, cx0, cy0); entI[pos] = (unsigned)p;
+          } else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) {
+            const unsigned pos = atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+            entE[pos] = pg_entry(a0, a1, b0, b1, cx, cy); entI[pos] = (unsigned)p;
+          }
+        }
+        __syncthreads();
+        // the tail of every list up to its group-of-4 boundary gets the never-matching word 0 (lists are scanned 4 entries per load)
+        for (int c = tid; c < ncell; c += kGridBlock) { const unsigned e = cells[c]; for (unsigned k = e; k < ((e + 3u) & ~3u); ++k) entE[k] = 0u; }
+        __syncthreads();
+        break;
+      }
+      if (G == 1) { if (tid == 0) gs.use_grid = 0; __syncthreads(); break; }              // cannot happen (cap >= F), kept as a guard
+      if (tid == 0) pg_coarsen(gs.fr);
+      __syncthreads();
+    }
+    // ---------------- pass 3: samples
+    const bool grid = gs.use_grid != 0;
+    const PGridFrame fr = gs.fr;
+    const int G = fr.G;
+    for (int base = warp * 32; base < F; base += kGridBlock) {
+      const int p = base + lane;
+      const bool active = p < F;
+      TriRegs t; t.prim = 0;
+      bool culled = true;
+      if (active) {
+        load_tri<HAS_VN, HAS_VA>(sc, p, t);
+        culled = false;
+        if (!HAS_VN && !P.sr) {                                   // same exact-safe plane-side cull as k_forward
+          const f3 w1 = t.st.v1 - o, w2 = t.st.v2 - o, w3 = t.st.v3 - o;
+          const float m1 = 1e-5f * (fabsf(w1.x) + fabsf(w1.y) + fabsf(w1.z));
+          culled = dot3(t.st.nf, w1) > m1 && dot3(on, w1) > m1 &&
+                   dot3(on, w2) > 1e-5f * (fabsf(w2.x) + fabsf(w2.y) + fabsf(w2.z)) &&
+                   dot3(on, w3) > 1e-5f * (fabsf(w3.x) + fabsf(w3.y) + fabsf(w3.z));
+        }
+      }
+      if (__all_sync(0xffffffffu, culled)) {
+        if (WRITE_VIS && lane == 0) for (int k = 0; k < P.spp; ++k) vis[(size_t)(s * P.spp + k) * P.words_per_row + (base >> 5)] = 0u;
+        continue;
+      }
+      for (int k = 0; k < P.spp; ++k) {
+        bool need = false; float val = 0.f, ts = 0.f; int bin = -1; f3 d = mk3(0.f, 0.f, 1.f);
+        if (!culled) {
+          SampleGeom g;
+          const TriRec trr = make_tri(t.st.v1, t.st.v2, t.st.v3);
+          if (draw_sample(P, P.src_offset + s, t.prim, k, o, t.st, trr, g) && g.r <= ub_half && g.r >= lb_half) {
+            const f3 n = shading_normal<HAS_VN>(t, g);
+            const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
+            if (P.sr ? ff != 0.0f : ff > 0.0f) {
+              const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
+              val = t.st.A * alb * ff * ff;
+              if (GGX) val = val * ggx_eval(P.alpha, dot3(n, -g.d));              // ggx/TG.cpp:236-238
+              if (MODE == 0) {
+                const int64_t b = (int64_t)floorf((2.0f * g.r - P.lb) / P.res_fwd);   // TG.cpp:229
+                bin = (b >= 0 && b < nbf) ? (int)b : -1;
+              }
+              need = true; d = g.d; ts = g.t;
+            }
+          }
+        }
+        bool occ = false;
+        if (grid) {
+          // a ray that does not point into the picture's half space (n_o.d <= 0 can only happen with an unclamped form factor)
+          // takes the BVH query
+          const bool in_picture = need && dot3(d, fr.n) > 0.0f;
+          if (need && !in_picture) occ = occluded(sc.nodes, sc.ttris, sc.root_count, make_ray(o, d), ts, t.prim);
+          int cx = 0, cy = 0; unsigned R = 0u;
+          if (in_picture) pg_ray(fr, d, cx, cy, R);
+          // this lane's list: groups of 4 entry words, 16-byte aligned (cells[] holds the END of every list after pass 2)
+          int start = 0, ngrp = 0;
+          if (in_picture) {
+            // slices 0 .. kr of the ray's picture cell are contiguous: one scan range (the padding words between them never match)
+            const int kr = pg_quant(ts * dot3(d, fr.n) + gs.pad_z, gs.z0, gs.sz, (float)(kGridK - 1));
+            const int c = (cy * G + cx) * kGridK; start = c ? (int)((cells[c - 1] + 3u) & ~3u) : 0; ngrp = ((int)cells[c + kr] - start + 3) >> 2;
+          }
+          const uint4* __restrict__ lst = reinterpret_cast<const uint4*>(entE + start);
+          // the warp's rays, readable by every lane: the exact tests below are pooled over the warp
+          gw.dx[lane] = d.x; gw.dy[lane] = d.y; gw.dz[lane] = d.z; gw.ts[lane] = ts; gw.prim[lane] = t.prim;
+          if (lane == 0) gw.occ = 0u;
+          __syncwarp();
+          const int maxg = __reduce_max_sync(0xffffffffu, ngrp);
+          for (int g0 = 0; g0 < maxg; g0 += 8) {                                  // 32 entries per lane and round
+            unsigned mask = 0u;
+            if (g0 < ngrp && !((gw.occ >> lane) & 1u)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (g0 + i < ngrp) {
+                  const uint4 e = lst[g0 + i];
+                  if (pg_precheck(e.x, R)) mask |= 1u << (4 * i);
+                  if (pg_precheck(e.y, R)) mask |= 2u << (4 * i);
+                  if (pg_precheck(e.z, R)) mask |= 4u << (4 * i);
+                  if (pg_precheck(e.w, R)) mask |= 8u << (4 * i);
+                }
+              }
+            }
+            // pooled exact tests: every lane hands up to kGridPush candidates to the warp's pool, then all 32 lanes work the pool
+            while (__any_sync(0xffffffffu, mask != 0u)) {
+              const int nb = __popc(mask);
+              const int n = nb < kGridPush ? nb : kGridPush;
+              int incl = n;
+#pragma unroll
+              for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += y; }
+              const int total = __shfl_sync(0xffffffffu, incl, 31);
+              int off = incl - n;
+              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | (unsigned)(start + 4 * g0 + bpos); }
+              __syncwarp();
+              for (int i = lane; i < total; i += 32) {
+                const unsigned item = gw.pool[i];
+                const int rl = (int)(item >> 27);
+                if (!((gw.occ >> rl) & 1u)) {
+                  const int tj = (int)entI[item & 0x7ffffffu];
+                  if (tj != base + rl && tri_occludes_od(sc.ttris, tj, o, mk3(gw.dx[rl], gw.dy[rl], gw.dz[rl]), gw.ts[rl], gw.prim[rl])) atomicOr(&gw.occ, 1u << rl);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          __syncwarp();
+          occ = occ || ((gw.occ >> lane) & 1u);
+          __syncwarp();                                                             // gw is rewritten by the next sample
+        } else if (need) {
+          occ = occluded(sc.nodes, sc.ttris, sc.root_count, make_ray(o, d), ts, t.prim);
+        }
+        const bool visible = need && !occ;
+        if (visible) {
+          const double dv = P.spp == 1 ? (double)val : (double)val / (double)P.spp;   // TG.cpp:231-232
+          if (MODE == 1) atomicAdd(out + t.prim, dv);
+          else if (bin >= 0) {
+            if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
+            else {
+              const int half = 2 * P.r_fwd * P.s_bin;
+              int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);
+              if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+              for (int b = b0; b <= b1; ++b) {
+                int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
+                if (ihi > ilo) atomicAdd(out + s * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
+              }
+            }
+          }
+        }
+        if (WRITE_VIS) {
+          const unsigned m = __ballot_sync(0xffffffffu, visible);
+          if (lane == 0) vis[(size_t)(s * P.spp + k) * P.words_per_row + (base >> 5)] = m;
+        }
+      }
+    }
+    __syncthreads();       // the next source reuses the cell array, the frame and the scratch arrays
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- K3 residual
 // diff = (data - T) [-> 2 d^3 if loss_flag] * weight      (SSG.cpp:543-550)
 __global__ void k_residual(const double* __restrict__ data, const double* __restrict__ weight, const double* __restrict__ T, double* __restrict__ diff, size_t n, int loss_flag) {
@@ -508,8 +837,45 @@ inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
   return dim3((unsigned)((sc.F + kBlock - 1) / kBlock), (unsigned)((P.L + P.chunk - 1) / P.chunk), 1);
 }
 
+// shared memory of k_forward_grid for a G x G grid
+inline size_t grid_smem_bytes(int G, bool smooth, int K) {
+  return ((sizeof(GridShared) + 15) & ~size_t(15)) + (smooth ? (((size_t)(K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0) +
+         (size_t)(kGridBlock / 32) * sizeof(GridWarp) + (size_t)G * G * kGridK * sizeof(unsigned);
+}
+// perspective-grid forward kernel: applies outside the first-generation mode (its unclamped form factor traces rays behind the wall point)
+inline bool use_grid_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
+  if (cx.forward_algo == 1 || P.sr || sc.F < 1 || sc.V < 1 || sc.bounds == nullptr || sc.verts == nullptr) return false;
+  return true;
+}
+template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
+void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+  const int sms = cx.num_sms > 0 ? cx.num_sms : 148;
+  const size_t budget = (size_t)(NLOS_GRID_MINBLOCKS >= 2 ? 113 : 226) * 1024;          // dynamic shared memory per block at the wanted residency
+  int G = cx.grid_res > 0 ? cx.grid_res : (int)(std::sqrt((double)sc.F * std::min(P.spp, 16)) * 0.25 + 0.5);   // ~16 samples per picture cell (measured optima: C-bunny G = 64, C-arm G = 16..32)
+  if (G < 1) G = 1;
+  if (G > 256) G = 256;                                                                  // quantised coordinates are 15-bit
+  while (G > 1 && grid_smem_bytes(G, SMOOTH, P.K) > budget) --G;
+  const size_t smem = grid_smem_bytes(G, SMOOTH, P.K);
+  const int blocks = (int)std::min<int64_t>(P.L, (int64_t)sms * NLOS_GRID_MINBLOCKS);
+  const unsigned cap = (unsigned)(std::min<int64_t>((int64_t)6 * sc.F + 4 * (int64_t)G * G * kGridK + 1024, 0x7fffff0) & ~(int64_t)3);     // entry positions are 27-bit, lists 16-byte aligned
+  GridScratch scr;
+  scr.proj = cx.buf("grid_proj").as<float4>((size_t)blocks * sc.V);
+  scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
+  scr.entE = cx.buf("grid_entE").as<unsigned>((size_t)blocks * cap);
+  scr.entI = cx.buf("grid_entI").as<unsigned>((size_t)blocks * cap);
+  if (vis) {
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, cap, G);
+  } else {
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, cap, G);
+  }
+  cx.launches += 1;
+}
+
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+  if (use_grid_forward(cx, sc, P)) { launch_forward_grid_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
   const dim3 grid((unsigned)((sc.F + 31) / 32), (unsigned)std::min<int64_t>((nchunks + kFwdBlock / 32 - 1) / (kFwdBlock / 32), 65535), 1);
   const size_t smem = (kFwdBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
