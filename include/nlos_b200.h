@@ -51,7 +51,16 @@ int nlos_ctx_set_seed(nlos_ctx* ctx, uint64_t seed);
 /* Sharded runs (one process per GPU): this call's sources are the global sources
  * [src_offset, src_offset + numSources); gradients are normalised by num_sources_global (0 = by numSources). */
 int nlos_ctx_set_source_window(nlos_ctx* ctx, int64_t src_offset, int64_t num_sources_global);
-/* keys: "reuse_visibility" (1), "chunk_forward" (0 = auto), "chunk_gradient" (0 = auto), "timing" (0) */
+/* Ordering against a caller's CUDA stream (only matters for DEVICE-pointer arguments, which are used in place on the context's own
+ * non-blocking stream): nlos_ctx_wait_stream makes all later work of the context wait for everything enqueued on `stream` so far
+ * (inputs written by the caller's kernels are seen); nlos_ctx_signal_stream makes `stream` wait for everything the context has
+ * enqueued so far (the caller's later kernels see the outputs).  `stream` is a cudaStream_t (NULL = the legacy default stream).
+ * The Python modules call both around every entry point that receives a torch CUDA tensor. */
+int nlos_ctx_wait_stream(nlos_ctx* ctx, void* stream);
+int nlos_ctx_signal_stream(nlos_ctx* ctx, void* stream);
+/* keys: "reuse_visibility" (1), "chunk_forward" (0 = auto), "chunk_gradient" (0 = auto), "timing" (0),
+ *       "forward_algo" (0 = auto, 1 = BVH traversal kernel, 2 = per-source perspective-grid kernel), "grid_res" (0 = auto: cells per
+ *       axis of the perspective grid), "grid_cap" (0 = none; test hook: entry budget of the grid per wall point) */
 int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value);
 /* ms of the last call: {scene build, forward, residual, gradient, total}; needs option "timing" = 1 */
 int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5);
@@ -221,6 +230,11 @@ int nlos_barycentric_to_world(nlos_ctx* ctx, const float* verticesD, int num_ver
                               const float* barycoord, int num_ray, float* intersection_p);
 
 /* ---- test / profiling hooks ------------------------------------------------------------------------ */
+
+/* TEST / DEBUG: the visibility words the forward pass of the LAST gradient call left for its gradient pass (one bit per sample:
+ * word [(source*spp + k) * ceil(F/32) + w], bit l = Morton-ordered triangle 32*w + l).  n_available receives the word count;
+ * out may be NULL to query it.  Used by the tests to show that the two forward kernels decide every sample identically. */
+int nlos_debug_copy_visibility_words(nlos_ctx* ctx, uint32_t* out, int64_t n, int64_t* n_available);
 
 /* Pure-geometry per-sample visibility (nearest hit == sampled triangle, TG.cpp:206) as bytes [L,F,spp];
  * counters (nullable, host) = {rays traced, box tests, triangle tests}. */

@@ -3,7 +3,9 @@
 The reference's Cython signatures take typed, C-contiguous NumPy buffers
 (`np.ndarray[float, ndim=2, mode='c']`, smoothed_transient/renderer.pyx:13-200): a wrong dtype / layout
 raises ValueError there, a wrong shape raises AssertionError.  The same rules apply here; additionally a
-torch CUDA tensor of the same dtype/shape is accepted wherever an array is, and is used in place (no copy).
+torch CUDA tensor of the same dtype/shape is accepted wherever an array is, and is used in place (no copy);
+the call is then ordered against torch's current stream on both sides (see _ffi._LibProxy), so tensors just written by
+torch ops are read correctly and torch ops enqueued after the call see its outputs.
 """
 import ctypes as C
 import math
@@ -11,6 +13,12 @@ import numpy as np
 
 _NP = {'f32': np.float32, 'i32': np.int32, 'f64': np.float64, 'u8': np.uint8}
 _CT = {'f32': C.c_float, 'i32': C.c_int, 'f64': C.c_double, 'u8': C.c_uint8}
+
+
+# stream of the torch CUDA tensors seen by as_pointer() since the last C-ABI call of this thread: _ffi's library proxy orders the
+# context's stream against it (nlos_ctx_wait_stream before the call, nlos_ctx_signal_stream after) and clears it
+import threading
+tls = threading.local()
 
 
 def _is_torch(a):
@@ -32,6 +40,8 @@ def as_pointer(a, kind, ndim, name, allow_none=False):
             raise ValueError('Buffer has wrong number of dimensions for %s (expected %d, got %d)' % (name, ndim, a.dim()))
         if not a.is_contiguous():
             raise ValueError('%s: tensor is not C-contiguous' % name)
+        if a.is_cuda:
+            tls.cuda_stream = torch.cuda.current_stream(a.device).cuda_stream
         return C.cast(C.c_void_p(a.data_ptr()), C.POINTER(_CT[kind])), tuple(a.shape)
     if not isinstance(a, np.ndarray):
         raise TypeError('Argument %s has incorrect type (expected numpy.ndarray, got %s)' % (name, type(a).__name__))

@@ -37,6 +37,8 @@ SIGNATURES = {
     'nlos_ctx_set_seed': (C.c_int, [_ctx, C.c_uint64]),
     'nlos_ctx_set_source_window': (C.c_int, [_ctx, C.c_int64, C.c_int64]),
     'nlos_ctx_set_option': (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
+    'nlos_ctx_wait_stream': (C.c_int, [_ctx, C.c_void_p]),
+    'nlos_ctx_signal_stream': (C.c_int, [_ctx, C.c_void_p]),
     'nlos_ctx_get_timing': (C.c_int, [_ctx, _f]),
     'nlos_ctx_launch_count': (C.c_uint64, [_ctx]),
     'nlos_ctx_set_external_samples': (C.c_int, [_ctx, _f, C.c_int64]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     'nlos_barycentric_to_world': (C.c_int, [_ctx, _f, C.c_int, _i, C.c_int, _f, C.c_int, _f]),
     'nlos_microbench_fp32': (C.c_double, [_ctx]),
     'nlos_microbench_red_f64': (C.c_double, [_ctx, C.c_int64]),
+    'nlos_debug_copy_visibility_words': (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_int64)]),
     'nlos_debug_visibility': (C.c_int, [_ctx, _f, C.c_int, _f, C.c_int, _i, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
 }
 
@@ -96,11 +99,43 @@ def load_library(path=None):
         return lib
 
 
+class _LibProxy(object):
+    """The library as a Context sees it.  Entry points that received torch CUDA tensors (noted by _arrays.as_pointer in a
+    thread-local) are ordered against torch's current stream: the context's stream waits for it before the call, and it waits
+    for the context's stream after the call — the device-pointer path of the C ABI runs on the context's own non-blocking
+    stream and would otherwise race with the caller's kernels on both sides."""
+
+    def __init__(self, lib, owner):
+        self._lib = lib; self._owner = owner; self._cache = {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name.startswith('nlos_ctx_') or name in ('nlos_last_error',):
+            return fn
+        w = self._cache.get(name)
+        if w is None:
+            from . import _arrays
+            lib, owner = self._lib, self._owner
+
+            def w(*args, _fn=fn):
+                st = getattr(_arrays.tls, 'cuda_stream', None)
+                _arrays.tls.cuda_stream = None
+                if st is None:
+                    return _fn(*args)
+                lib.nlos_ctx_wait_stream(owner.handle, C.c_void_p(st))
+                try:
+                    return _fn(*args)
+                finally:
+                    lib.nlos_ctx_signal_stream(owner.handle, C.c_void_p(st))
+            self._cache[name] = w
+        return w
+
+
 class Context(object):
     """Owns one nlos_ctx (stream + scratch buffers) on one GPU."""
 
     def __init__(self, device=0):
-        self.lib = load_library()
+        self.lib = _LibProxy(load_library(), self)
         h = _ctx()
         rc = self.lib.nlos_ctx_create(int(device), C.byref(h))
         if rc != NLOS_OK:
@@ -139,6 +174,16 @@ class Context(object):
         buf = (C.c_float * 5)()
         self.check(self.lib.nlos_ctx_get_timing(self.handle, buf), 'nlos_ctx_get_timing')
         return dict(zip(('build_ms', 'forward_ms', 'residual_ms', 'gradient_ms', 'total_ms'), [float(x) for x in buf]))
+
+    def visibility_words(self):
+        """DEBUG: the visibility words of the last gradient call (see include/nlos_b200.h)."""
+        import numpy as np
+        n = C.c_int64(0)
+        self.check(self.lib.nlos_debug_copy_visibility_words(self.handle, None, 0, C.byref(n)), 'nlos_debug_copy_visibility_words')
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            self.check(self.lib.nlos_debug_copy_visibility_words(self.handle, out.ctypes.data_as(C.POINTER(C.c_uint32)), n.value, None), 'nlos_debug_copy_visibility_words')
+        return out
 
     def launch_count(self):
         return int(self.lib.nlos_ctx_launch_count(self.handle))

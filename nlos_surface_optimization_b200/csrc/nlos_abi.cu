@@ -22,6 +22,7 @@ Ctx::~Ctx() {
   if (ev_copy) cudaEventDestroy(ev_copy);
   if (ev_fwd) cudaEventDestroy(ev_fwd);
   if (ev_start) cudaEventDestroy(ev_start);
+  if (ev_ext) cudaEventDestroy(ev_ext);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -225,7 +226,8 @@ void run_job(Ctx& cx, const Job& j_in) {
       // ---- K1: forward (+ visibility bits for the gradient pass)
       uint32_t* vis = nullptr;
       const bool want_grad = j.kind >= 0 && j.kind <= 2;
-      if (want_grad && cx.reuse_visibility) vis = cx.buf("vis").as<uint32_t>((size_t)j.L * P.spp * P.words_per_row);
+      cx.vis_words = 0;
+      if (want_grad && cx.reuse_visibility) { cx.vis_words = (size_t)j.L * P.spp * P.words_per_row; vis = cx.buf("vis").as<uint32_t>(cx.vis_words); }
       P.chunk = forward_chunk(cx);                                                       // sample slots per warp pass
       const double* d_jw = nullptr; const double* d_jg = nullptr;
       if (j.jlen > 0) {
@@ -357,6 +359,7 @@ int nlos_ctx_create(int device, nlos_ctx** out) {
     NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_copy, cudaEventDisableTiming));
     NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_fwd, cudaEventDisableTiming));
     NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_start, cudaEventDisableTiming));
+    NLOS_CUDA_OK(cudaEventCreateWithFlags(&c->cx.ev_ext, cudaEventDisableTiming));
   } catch (const std::exception& ex) { g_create_error = ex.what(); delete c; return NLOS_ERR_CUDA; }
   *out = c;
   return NLOS_OK;
@@ -372,6 +375,28 @@ int nlos_ctx_synchronize(nlos_ctx* ctx) {
   return NLOS_OK;
 }
 void* nlos_ctx_stream(nlos_ctx* ctx) { return ctx ? (void*)ctx->cx.stream : nullptr; }
+int nlos_ctx_wait_stream(nlos_ctx* ctx, void* stream) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  if ((cudaStream_t)stream == cx.stream) return NLOS_OK;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_CUDA_OK(cudaEventRecord(cx.ev_ext, (cudaStream_t)stream));
+    NLOS_CUDA_OK(cudaStreamWaitEvent(cx.stream, cx.ev_ext, 0));
+    return NLOS_OK;
+  } catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+int nlos_ctx_signal_stream(nlos_ctx* ctx, void* stream) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  if ((cudaStream_t)stream == cx.stream) return NLOS_OK;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_CUDA_OK(cudaEventRecord(cx.ev_ext, cx.stream));
+    NLOS_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, cx.ev_ext, 0));
+    return NLOS_OK;
+  } catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
 int nlos_ctx_set_seed(nlos_ctx* ctx, uint64_t seed) { if (!ctx) return NLOS_ERR_INVALID; ctx->cx.seed = seed; return NLOS_OK; }
 int nlos_ctx_set_external_samples(nlos_ctx* ctx, const float* st, int64_t n) {
   if (!ctx || n < 0 || (n > 0 && !st)) return NLOS_ERR_INVALID;
@@ -402,6 +427,7 @@ int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value) {
   else if (k == "chunk_gradient") ctx->cx.chunk_gradient = (int)value;
   else if (k == "timing") ctx->cx.timing_enabled = value != 0;
   else if (k == "forward_algo") { if (value < 0 || value > 2) { ctx->cx.last_error = "forward_algo must be 0 (auto), 1 (bvh) or 2 (grid)"; return NLOS_ERR_INVALID; } ctx->cx.forward_algo = (int)value; }
+  else if (k == "grid_cap") { if (value < 0 || value > 0x7fffffff) { ctx->cx.last_error = "grid_cap out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_cap = (int)value; }
   else if (k == "grid_res") { if (value < 0 || value > 4096) { ctx->cx.last_error = "grid_res out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_res = (int)value; }
   else { ctx->cx.last_error = "unknown option " + k; return NLOS_ERR_INVALID; }
   return NLOS_OK;
@@ -660,6 +686,23 @@ int nlos_barycentric_to_world(nlos_ctx* ctx, const float* verticesD, int num_ver
     OutView<float> o_out = stage_out(cx, "out_world", intersection_p, 3 * (size_t)num_ray, true);   // misses stay untouched
     launch_bary_to_world(cx, d_verts, d_faces, d_b, num_ray, o_out.dev);
     if (finish_out(cx, o_out)) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    cx.last_error.clear();
+    return NLOS_OK;
+  } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }
+  catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
+
+int nlos_debug_copy_visibility_words(nlos_ctx* ctx, uint32_t* out, int64_t n, int64_t* n_available) {
+  if (!ctx) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_CUDA_OK(cudaStreamSynchronize(cx.stream));
+    if (n_available) *n_available = (int64_t)cx.vis_words;
+    if (out && n > 0) {
+      NLOS_REQUIRE((size_t)n <= cx.vis_words, "more words requested than the last gradient call produced");
+      NLOS_CUDA_OK(cudaMemcpy(out, cx.buf("vis").p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
     cx.last_error.clear();
     return NLOS_OK;
   } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }

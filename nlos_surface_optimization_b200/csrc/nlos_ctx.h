@@ -36,6 +36,7 @@ struct Ctx {
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_copy = nullptr;   // data/weight staged on copy_stream
   cudaEvent_t ev_start = nullptr;  // start of the current call on the main stream
+  cudaEvent_t ev_ext = nullptr;    // ordering against a caller's stream (nlos_ctx_wait_stream / nlos_ctx_signal_stream)
   cudaEvent_t ev_fwd = nullptr;    // forward transient final (its D2H may start while the gradient runs)
   std::string last_error;
   // options (nlos_ctx_set_*)
@@ -49,6 +50,8 @@ struct Ctx {
   int chunk_gradient = 0;        // same for the gradient pass
   int forward_algo = 0;          // 0 auto (perspective grid where it applies), 1 BVH traversal kernel, 2 perspective grid
   int grid_res = 0;              // cells per axis of the perspective grid (0 = auto from the triangle count)
+  int grid_cap = 0;              // test hook: upper bound of the per-source entry budget of the perspective grid (0 = none); forces the coarsening path
+  size_t vis_words = 0;          // words of the last call's visibility buffer (nlos_debug_copy_visibility_words)
   int num_sms = 0;               // multiprocessors of the device (filled at context creation)
   Timing timing;
   uint64_t launches = 0;         // kernels launched by this context (bench.py's gpu_launches)

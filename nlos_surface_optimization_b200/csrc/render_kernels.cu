@@ -845,7 +845,9 @@ inline size_t grid_smem_bytes(int G, bool smooth, int K) {
 // perspective-grid forward kernel: applies outside the first-generation mode (its unclamped form factor traces rays behind the wall point)
 inline bool use_grid_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
   if (cx.forward_algo == 1 || P.sr || sc.F < 1 || sc.V < 1 || sc.bounds == nullptr || sc.verts == nullptr) return false;
-  return true;
+  if (cx.forward_algo == 2) return true;
+  // auto: one block per wall point needs enough wall points to fill the machine; below that the BVH kernel (finer work items) is used
+  return P.L >= (cx.num_sms > 0 ? cx.num_sms : 148);
 }
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
@@ -858,6 +860,8 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   const size_t smem = grid_smem_bytes(G, SMOOTH, P.K);
   const int blocks = (int)std::min<int64_t>(P.L, (int64_t)sms * NLOS_GRID_MINBLOCKS);
   const unsigned cap = (unsigned)(std::min<int64_t>((int64_t)6 * sc.F + 4 * (int64_t)G * G * kGridK + 1024, 0x7fffff0) & ~(int64_t)3);     // entry positions are 27-bit, lists 16-byte aligned
+  unsigned capv = cap;
+  if (cx.grid_cap > 0) capv = (unsigned)std::max<int64_t>(std::min<int64_t>(cap, cx.grid_cap), ((int64_t)sc.F + 3 + 4 * kGridK) & ~(int64_t)3);   // never below one coarsest-grid fill
   GridScratch scr;
   scr.proj = cx.buf("grid_proj").as<float4>((size_t)blocks * sc.V);
   scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
@@ -865,10 +869,10 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   scr.entI = cx.buf("grid_entI").as<unsigned>((size_t)blocks * cap);
   if (vis) {
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, cap, G);
+    k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);
   } else {
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, cap, G);
+    k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);
   }
   cx.launches += 1;
 }

@@ -931,3 +931,107 @@ int nlos_oracle_jitter_gradient(const double* data, const double* weight, const 
   return 0;
 }
 }
+
+// ==================================================================================== canonical traversal counter
+// The accounting unit of bench.py's FP32 roofline: box and triangle tests per ray of the CANONICAL traversal SURVEY.md 8(d) defines —
+// binary LBVH (30-bit Morton code of the AABB centroid, Karras-2012 topology, ONE triangle per leaf), single-ray stack traversal,
+// near child first, cull on t_enter > t_best, nearest hit — run over every path sample (source, triangle, k) of the given sources.
+// It defines work, it is not an implementation anybody ships (the checker above uses a median-split tree, the CUDA path a
+// perspective grid or a 4-per-leaf LBVH).  Own restatement of Karras (2012), "Maximizing parallelism in the construction of BVHs".
+namespace canon {
+struct CNode { Box b[2]; int child[2]; };           // child >= 0: internal node, < 0: leaf ~child (sorted triangle position)
+static inline uint32_t expand10(uint32_t v) { v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu; v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u; return v; }
+static inline int delta(const std::vector<uint64_t>& k, int i, int j) { if (j < 0 || j >= (int)k.size()) return -1; return __builtin_clzll(k[i] ^ k[j]); }
+struct Tree { std::vector<CNode> nodes; std::vector<int> order; };
+static void build(const Scene& sc, Tree& t) {
+  const int F = sc.F; std::vector<Box> bx(F); V3 lo = mk(3e38f, 3e38f, 3e38f), hi = mk(-3e38f, -3e38f, -3e38f);
+  std::vector<V3> cen(F);
+  for (int f = 0; f < F; ++f) { bx[f] = tri_box(sc, f); cen[f] = (bx[f].lo + bx[f].hi) * 0.5f; lo = mk(std::min(lo.x, cen[f].x), std::min(lo.y, cen[f].y), std::min(lo.z, cen[f].z)); hi = mk(std::max(hi.x, cen[f].x), std::max(hi.y, cen[f].y), std::max(hi.z, cen[f].z)); }
+  std::vector<uint64_t> keys(F);
+  auto q = [](float x, float l, float h) { float e = std::max(h - l, 1e-30f); float v = (x - l) / e * 1024.0f; return (uint32_t)std::min(std::max(v, 0.0f), 1023.0f); };
+  for (int f = 0; f < F; ++f) keys[f] = ((uint64_t)((expand10(q(cen[f].x, lo.x, hi.x)) << 2) | (expand10(q(cen[f].y, lo.y, hi.y)) << 1) | expand10(q(cen[f].z, lo.z, hi.z))) << 32) | (uint32_t)f;
+  std::sort(keys.begin(), keys.end());
+  t.order.resize(F); for (int p = 0; p < F; ++p) t.order[p] = (int)(uint32_t)keys[p];
+  const int NI = F - 1; t.nodes.assign(std::max(NI, 0), CNode());
+  std::vector<int> parent(NI, -1), lparent(F, -1);
+  for (int i = 0; i < NI; ++i) {
+    const int d = (delta(keys, i, i + 1) - delta(keys, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, i, i - d);
+    int lmax = 2; while (delta(keys, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0; for (int tt = lmax >> 1; tt >= 1; tt >>= 1) if (delta(keys, i, i + (l + tt) * d) > dmin) l += tt;
+    const int j = i + l * d, dn = delta(keys, i, j);
+    int sp = 0; for (int tt = (l + 1) >> 1;; tt = (tt + 1) >> 1) { if (delta(keys, i, i + (sp + tt) * d) > dn) sp += tt; if (tt <= 1) break; }
+    const int split = i + sp * d + std::min(d, 0), a = std::min(i, j), b = std::max(i, j);
+    if (a == split) { t.nodes[i].child[0] = ~split; lparent[split] = i; } else { t.nodes[i].child[0] = split; parent[split] = i; }
+    if (b == split + 1) { t.nodes[i].child[1] = ~(split + 1); lparent[split + 1] = i; } else { t.nodes[i].child[1] = split + 1; parent[split + 1] = i; }
+  }
+  // boxes bottom-up (children before parents: process by decreasing depth via a DFS order)
+  std::vector<int> dfs; dfs.reserve(NI); if (NI > 0) { std::vector<int> st(1, 0); while (!st.empty()) { int n = st.back(); st.pop_back(); dfs.push_back(n); for (int c = 0; c < 2; ++c) if (t.nodes[n].child[c] >= 0) st.push_back(t.nodes[n].child[c]); } }
+  std::vector<Box> nb(NI);
+  for (int k = (int)dfs.size() - 1; k >= 0; --k) { const int n = dfs[k]; for (int c = 0; c < 2; ++c) { const int ch = t.nodes[n].child[c]; t.nodes[n].b[c] = ch < 0 ? bx[t.order[~ch]] : nb[ch]; } nb[n] = merge(t.nodes[n].b[0], t.nodes[n].b[1]); }
+}
+static inline bool slab(const Box& b, V3 o, V3 id, float tbest, float& tn) {
+  float tx1 = (b.lo.x - o.x) * id.x, tx2 = (b.hi.x - o.x) * id.x, ty1 = (b.lo.y - o.y) * id.y, ty2 = (b.hi.y - o.y) * id.y, tz1 = (b.lo.z - o.z) * id.z, tz2 = (b.hi.z - o.z) * id.z;
+  float tmn = std::max(std::max(std::min(tx1, tx2), std::min(ty1, ty2)), std::max(std::min(tz1, tz2), 0.0f));
+  float tmx = std::min(std::min(std::max(tx1, tx2), std::max(ty1, ty2)), std::max(tz1, tz2));
+  tn = tmn; return tmn <= tmx && tmn <= tbest;
+}
+// nearest hit with counters; returns the primitive
+static int trace(const Scene& sc, const Tree& t, V3 o, V3 d, uint64_t& nbox, uint64_t& ntri) {
+  int best = -1; float tb = std::numeric_limits<float>::infinity();
+  auto leaf = [&](int pos) { const int f = t.order[pos]; float tt, u, v; ++ntri; if (isect(sc.tris[f], o, d, tt, u, v) && (tt < tb || (tt == tb && f < best))) { tb = tt; best = f; } };
+  if (sc.F == 1) { leaf(0); return best; }
+  V3 id = mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  int stack[128]; float tstack[128]; int sp = 0; stack[sp] = 0; tstack[sp++] = 0.f;
+  while (sp) {
+    const int c = stack[--sp];
+    if (tstack[sp] > tb) continue;                                       // cull on t_enter > t_best
+    if (c < 0) { leaf(~c); continue; }
+    const CNode& nd = t.nodes[c]; float t0, t1; nbox += 2;
+    const bool h0 = slab(nd.b[0], o, id, tb, t0), h1 = slab(nd.b[1], o, id, tb, t1);
+    if (h0 && h1) {                                                      // near child first: push the far one below it
+      const bool first0 = t0 <= t1;
+      stack[sp] = nd.child[first0 ? 1 : 0]; tstack[sp++] = first0 ? t1 : t0;
+      stack[sp] = nd.child[first0 ? 0 : 1]; tstack[sp++] = first0 ? t0 : t1;
+    } else if (h0) { stack[sp] = nd.child[0]; tstack[sp++] = t0; }
+    else if (h1) { stack[sp] = nd.child[1]; tstack[sp++] = t1; }
+  }
+  return best;
+}
+}  // namespace canon
+
+extern "C" {
+// out[0..3] = path samples (rays), box tests, triangle tests, visible samples — canonical nearest-hit traversal over every
+// (source, triangle, k) sample of the given sources
+int nlos_oracle_canonical_counts(const float* origin, int64_t L, const float* verts, int V, const int32_t* faces, int F, int num_samples,
+                                 uint64_t seed, int64_t src_offset, uint64_t* out4) {
+  if (F <= 0 || L <= 0) { out4[0] = out4[1] = out4[2] = out4[3] = 0; return 0; }
+  Scene sc; build_scene(sc, verts, V, faces, F, origin, L, true);
+  float scale = 0.f; for (int i = 0; i < 3 * V; ++i) scale = std::max(scale, fabsf(verts[i])); for (int64_t i = 0; i < 3 * L; ++i) scale = std::max(scale, fabsf(origin[i]));
+  sc.pad = scale * (1.0f / 65536.0f);                  // the device tree's padding
+  canon::Tree tree; canon::build(sc, tree);
+  const int spp = 1 + (num_samples - 1) / F;
+  uint64_t nr = 0, nb = 0, nt = 0, nv = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nr, nb, nt, nv)
+  for (int64_t s = 0; s < L; ++s) {
+    const V3 o = ld3(origin, s);
+    for (int f = 0; f < F; ++f) {
+      const V3 v1 = ld3(verts, faces[3 * f]), v2 = ld3(verts, faces[3 * f + 1]), v3 = ld3(verts, faces[3 * f + 2]);
+      for (int k = 0; k < spp; ++k) {
+        float S, T; sample_ST(seed, src_offset + s, f, k, S, T);
+        const float sq = sqrtf(T); const V3 point = blend3(1 - sq, v1, (1 - S) * sq, v2, S * sq, v3);
+        const V3 qd = point - o; const V3 d = qd * (1.0f / len3(qd));
+        uint64_t b = 0, t = 0; const int prim = canon::trace(sc, tree, o, d, b, t);
+        nr += 1; nb += b; nt += t; nv += prim == f;
+      }
+    }
+  }
+  out4[0] = nr; out4[1] = nb; out4[2] = nt; out4[3] = nv;
+  return 0;
+}
+void nlos_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+}  // extern "C"

@@ -266,3 +266,19 @@ def set_external_samples(stream):
         return
     _EXT = np.ascontiguousarray(stream, dtype=np.float32)
     lib().nlos_oracle_set_external_samples(_p(_EXT, C.c_float), C.c_int64(_EXT.size))
+
+
+def set_threads(n):
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py wants all host cores)."""
+    lib().nlos_oracle_set_threads(int(n))
+
+
+def canonical_counts(origin, vertices, faces, num_sample, seed=DEFAULT_SEED, src_offset=0):
+    """box / triangle tests per path sample of the canonical traversal (Karras LBVH, one triangle per leaf, near child
+    first, nearest hit) over every (source, triangle, k) sample of `origin`.  -> dict(rays, box_per_ray, tri_per_ray, visible_frac)."""
+    o = _f32(origin); v = _f32(vertices); f = np.ascontiguousarray(faces, dtype=np.int32)
+    out = (C.c_uint64 * 4)()
+    lib().nlos_oracle_canonical_counts(_p(o, C.c_float), C.c_int64(o.shape[0]), _p(v, C.c_float), C.c_int(v.shape[0]), _p(f, C.c_int32), C.c_int(f.shape[0]),
+                                       C.c_int(int(num_sample)), C.c_uint64(int(seed)), C.c_int64(int(src_offset)), out)
+    r = max(int(out[0]), 1)
+    return {'rays': int(out[0]), 'box_per_ray': out[1] / r, 'tri_per_ray': out[2] / r, 'visible_frac': out[3] / r}
