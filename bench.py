@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 transient renderer (contract: see the task statement / DESIGN.md "Measurement").
+"""bench.py — headline benchmark of the B200 transient renderer (contract: task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config bunny|ggx|arm|scale]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C-bunny"): bunny (F=69 630), 64x64 confocal wall, B=1200 bins of 1.2 mm,
-sample_num=20 000 (spp=1), refine_scale=10, sigma_bin=1, testing_flag=1, loss_flag=0.  One STEP = one
-renderStreamedGradient call = forward pass + residual + vertex-gradient pass (+ scene build, + NCCL all-reduce
-of the gradient when N>1) = 2*L*F*spp path samples.  N>1: each rank renders its own 64x64 slice of a (64N)x64
-wall (weak scaling), the gradient is all-reduced once per step.
+Default workload (BASELINE.json configs[1], "C-bunny"): bunny (F=69 630), 64x64 confocal wall, B=1200 bins of 1.2 mm,
+sample_num=20 000 (spp=1), refine_scale=10, sigma_bin=1, testing_flag=1, loss_flag=0.  One STEP = one renderStreamedGradient call =
+scene build + forward pass + residual + vertex-gradient pass (+ NCCL all-reduce of the gradient when N>1) = 2*L*F*spp path samples.
+N>1: each rank renders its own 64x64 slice of a (64N)x64 wall (weak scaling), the gradient is all-reduced once per step.
 
-Prints ONE JSON line (rank 0).  `value` = path samples/s with all inputs resident in HBM; `e2e` = the same through
-the C ABI with pinned HOST buffers (H2D/D2H inside the timed region).
+Prints ONE JSON line (rank 0).  `value` = path samples/s with all inputs resident in HBM; `e2e` = the same through the C ABI with
+pinned HOST buffers (H2D/D2H inside the timed region); `e2e_pageable` = the same with ordinary NumPy arrays, as the reference's
+callers allocate them.  Every number in the line is measured in this run (roofline numerator: the oracle's canonical traversal
+counter; `roofline.traffic`: the committed ncu capture of this command under profiles/).  The line also carries a
+`strong` sub-record: the named scaling config C-scale (F=500k, 256x256 wall, 2048 bins) and C-bunny with its 4096 wall points SPLIT
+over the N ranks, with a check of the all-reduced gradient against a single-rank recompute.
+
+Other configs print their own line on the same contract: `--config ggx` (BASELINE configs[2]), `--config arm` (configs[3]: the
+optimisation loop, ms per iteration next to the CPU baseline), `--config scale` (configs[4] as the headline line).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -31,21 +38,26 @@ SAMPLE_NUM, REFINE, SIGMA = 20000, 10, 1
 WALL = 64
 METRIC = 'transient path samples/sec (fwd+vertex grad)'
 UNIT = 'path samples/s'
+DTYPE = 'f32 math / f64 accumulation'
+# SURVEY 8(d) prices of the accounting (FP32 flops, FMA = 2)
+FL_GEN, FL_BOX, FL_TRI, FL_SHADE_FWD, FL_SHADE_BWD, FL_GGX_FWD, FL_GGX_BWD = 32, 23, 50, 48, 153, 30, 120
 
 
-def workload(rank, world):
-    from nlos_surface_optimization_b200 import scenes
-    v, f = scenes.bunny()
-    # (64*world) x 64 wall on [-.25,.25]^2; rank r owns the interleaved rows r, r+world, ... (every rank sees the whole
-    # wall extent => equal work per rank); global source index = rank*L + local index (RNG key, nlos_ctx_set_source_window)
-    lin_x = np.linspace(-.25, .25, WALL)
-    lin_y = np.linspace(-.25, .25, WALL * world)[rank::world]
-    gx, gy = np.meshgrid(lin_x, lin_y)
-    o = np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1).astype(np.float32))
-    L = o.shape[0]
-    L_global = L * world
-    n = np.ascontiguousarray(np.tile(np.array([0, 0, 1], dtype=np.float32), (L, 1)))
-    return o, n, v, f, L, L_global
+# ------------------------------------------------------------------------------------------------ workloads
+def wall_slice(rank, world, wall=WALL, weak=True):
+    """weak: a (wall*world) x wall wall, rank r owns the interleaved rows r, r+world, ... (every rank sees the whole wall extent =>
+    equal work per rank).  strong: the wall x wall wall, rank r owns a contiguous slice of its L points (dist.shard_range)."""
+    if weak:
+        lin_x = np.linspace(-.25, .25, wall)
+        lin_y = np.linspace(-.25, .25, wall * world)[rank::world]
+        gx, gy = np.meshgrid(lin_x, lin_y)
+        o = np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1).astype(np.float32))
+        n = np.ascontiguousarray(np.tile(np.array([0, 0, 1], dtype=np.float32), (o.shape[0], 1)))
+        return o, n, rank * o.shape[0], o.shape[0] * world
+    from nlos_surface_optimization_b200 import scenes, dist as nd
+    o, n = scenes.wall_grid(wall)
+    a, b = nd.shard_range(o.shape[0], rank, world)
+    return np.ascontiguousarray(o[a:b]), np.ascontiguousarray(n[a:b]), a, o.shape[0]
 
 
 class ClockSampler(threading.Thread):
@@ -84,45 +96,129 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def cpu_baseline(v, f, n_sources, want_stats=True, repeats=1):
-    """The oracle port (reference-restated CPU path, NOT the Embree build) on a bounded sample of the same workload."""
+class Microbench(object):
+    """benchlib/libnlos_microbench.so: measured FP32 / atomic roofline denominators (bench-only library, not the product ABI)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.lib = None
+        p = os.path.join(ROOT, 'benchlib', 'libnlos_microbench.so')
+        if os.path.exists(p):
+            self.lib = ctypes.CDLL(p)
+            self.lib.nlos_microbench_fp32.restype = ctypes.c_double; self.lib.nlos_microbench_fp32.argtypes = [ctypes.c_int]
+            self.lib.nlos_microbench_red_f64.restype = ctypes.c_double; self.lib.nlos_microbench_red_f64.argtypes = [ctypes.c_int, ctypes.c_int64]
+            self.lib.nlos_microbench_smem_atomic.restype = ctypes.c_double; self.lib.nlos_microbench_smem_atomic.argtypes = [ctypes.c_int, ctypes.c_int]
+
+    def fp32(self, sm_count):
+        if self.lib is not None:
+            v = float(self.lib.nlos_microbench_fp32(self.device))
+            if v > 0:
+                return v, 'measured in this run (FFMA chain, benchlib/microbench.cu)'
+        return sm_count * 128 * 2 * 1.965e9 / 1e12, 'nominal (SMs x 128 x 2 x 1965 MHz): benchlib/libnlos_microbench.so missing'
+
+    def red_f64(self, n):
+        v = float(self.lib.nlos_microbench_red_f64(self.device, int(n))) if self.lib is not None else -1.0
+        return v if v > 0 else None
+
+    def smem_atomic(self, n):
+        v = float(self.lib.nlos_microbench_smem_atomic(self.device, int(n))) if self.lib is not None else -1.0
+        return v if v > 0 else None
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def oracle_all_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core the box has."""
     from oracle import oracle
+    oracle.set_threads(os.cpu_count() or 1)
+    return oracle
+
+
+def cpu_gradient_rate(v, f, o, n, n_sources, sample_num=SAMPLE_NUM, alpha=None, numbins=None, refine=REFINE, sigma=SIGMA):
+    """The oracle port (reference-restated CPU path, NOT the Embree build) on `n_sources` wall points spread over the wall.
+    -> (path samples/s, threads, seconds)"""
+    oracle = oracle_all_threads()
+    idx = np.linspace(0, o.shape[0] - 1, min(n_sources, o.shape[0])).astype(int)       # spread over the wall, not one corner
+    oo = np.ascontiguousarray(o[idx]); nn = np.ascontiguousarray(n[idx])
+    ub = UB if numbins is None else numbins * RES
+    B = oracle.num_bins(LB, ub, RES)
+    data = np.zeros((len(idx), B)); weight = np.ones((len(idx), B))
+    kw = {} if alpha is None else {'alpha': alpha}
+    t0 = time.perf_counter()
+    oracle.gradient(oo, nn, v, f, sample_num, LB, ub, RES, data, weight, refine, sigma, 1, 0, **kw)
+    dt = time.perf_counter() - t0
+    spp = 1 + (sample_num - 1) // f.shape[0]
+    return 2 * len(idx) * f.shape[0] * spp / dt, oracle.threads(), dt
+
+
+def config_scene(cfg):
+    """-> dict(v, f, wall, sample_num, numbins, alpha, label) of a named config (full wall; ranks slice it themselves)."""
     from nlos_surface_optimization_b200 import scenes
-    o, n = scenes.wall_grid(WALL)
-    idx = np.linspace(0, o.shape[0] - 1, n_sources).astype(int)       # spread over the wall, not one corner
-    o = np.ascontiguousarray(o[idx]); n = np.ascontiguousarray(n[idx])
-    B = oracle.num_bins(LB, UB, RES)
-    data = np.zeros((n_sources, B)); weight = np.ones((n_sources, B))
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        oracle.gradient(o, n, v, f, SAMPLE_NUM, LB, UB, RES, data, weight, REFINE, SIGMA, 1, 0)
-        times.append(time.perf_counter() - t0)
-    spp = 1 + (SAMPLE_NUM - 1) // f.shape[0]
-    samples = 2 * n_sources * f.shape[0] * spp
-    stats = None
-    if want_stats:
-        st = oracle.transient(o[:8], n[:8], v, f, SAMPLE_NUM, LB, UB, RES, want_stats=True)[2]
-        stats = {'box_per_ray': st['box_tests'] / st['rays'], 'tri_per_ray': st['tri_tests'] / st['rays']}
-    return samples / min(times), oracle.threads(), times, stats
+    if cfg == 'bunny':
+        v, f = scenes.bunny()
+        return dict(v=v, f=f, wall=WALL, sample_num=SAMPLE_NUM, numbins=1200, alpha=None, label='C-bunny (bunny V=34817 F=69630, 64x64 wall, B=1200, spp=1, r=10, s=1)')
+    if cfg == 'ggx':
+        v, f = scenes.bunny()
+        return dict(v=v, f=f, wall=WALL, sample_num=SAMPLE_NUM, numbins=1200, alpha=0.1, label='C-ggx (bunny F=69630, GGX alpha=0.1, data rendered at alpha=0.2, 64x64 wall, B=1200, spp=1, r=10, s=1, testing_flag=1)')
+    if cfg == 'arm':
+        v, f = scenes.armadillo_init()
+        return dict(v=v, f=f, wall=WALL, sample_num=SAMPLE_NUM, numbins=1200, alpha=None, label='C-arm (armadillo init V=%d F=%d, fixed topology, 64x64 wall, B=1200, sample_num=20000 -> spp=18)' % (v.shape[0], f.shape[0]))
+    if cfg == 'scale':
+        v, f = scenes.heightfield(501)
+        return dict(v=v, f=f, wall=256, sample_num=f.shape[0], numbins=2048, alpha=None, label='C-scale (height field V=251001 F=500000, 256x256 wall, B=2048, spp=1, r=10, s=1)')
+    raise SystemExit('unknown --config %s' % cfg)
 
 
-def reference_build_rate(v, f, n_sources=32):
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores — the oracle port, the FASTER of the two CPU
+    implementations available (the other: the reference's own sources on stand-in library headers, oracle/_ref, reported under
+    `reference_build`) — on bounded samples of the workload sized so that the whole run stays under ~100 s at any N."""
+    if rank != 0:
+        return
+    from nlos_surface_optimization_b200 import scenes
+    sc = config_scene(args.config)
+    v, f = sc['v'], sc['f']
+    o, n = scenes.wall_grid(sc['wall'])
+    L = o.shape[0]
+    spp = 1 + (sc['sample_num'] - 1) // f.shape[0]
+    # size the per-step sample from a small probe: (steps + 1 warm-up) steps within the budget
+    rate0, threads, dt0 = cpu_gradient_rate(v, f, o, n, 8, sc['sample_num'], sc['alpha'], sc['numbins'])
+    budget_s = 80.0 / max(args.steps + 1, 1)
+    n_src = int(max(8, min(L, 256, rate0 * budget_s / (2 * f.shape[0] * spp))))
+    if args.warmup > 0:
+        cpu_gradient_rate(v, f, o, n, n_src, sc['sample_num'], sc['alpha'], sc['numbins'])
+    vals, times = [], []
+    for _ in range(args.steps):
+        val, threads, dt = cpu_gradient_rate(v, f, o, n, n_src, sc['sample_num'], sc['alpha'], sc['numbins'])
+        vals.append(val); times.append(dt)
+    value = float(np.mean(vals))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE,
+            'data': 'synthetic', 'config': {'workload': '%s; each step = %d of %d wall points' % (sc['label'], n_src, L)},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': '%d of %d wall points x all %d triangles, forward+gradient, OpenMP oracle on %d threads (reference-restated CPU path, not the Embree build)' % (n_src, L, f.shape[0], threads)},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'ms_per_iteration_extrapolated': 1e3 * (2 * L * f.shape[0] * spp) / value}
+    if args.config == 'bunny':
+        rb = reference_build_rate(v, f, o, n)
+        if rb is not None:
+            line['reference_build'] = rb
+    print(json.dumps(line), flush=True)
+
+
+def reference_build_rate(v, f, o, n, n_sources=16):
     """Throughput of the reference's OWN translation units (oracle/_ref, built against the stand-in Embree/TBB/MKL/Boost headers) on a
     small sample, for the record: its ray query is the stand-in's scalar BVH, so it is SLOWER than the port and not used as the arm."""
     try:
         from oracle import oracle, reference
         if not reference.available():
             return None
-        from nlos_surface_optimization_b200 import scenes
-        o, n = scenes.wall_grid(WALL)
         idx = np.linspace(0, o.shape[0] - 1, n_sources).astype(int)
-        o = np.ascontiguousarray(o[idx]); n = np.ascontiguousarray(n[idx])
+        oo = np.ascontiguousarray(o[idx]); nn = np.ascontiguousarray(n[idx])
         B = oracle.num_bins(LB, UB, RES)
         data = np.zeros((n_sources, B)); weight = np.ones((n_sources, B))
         reference.set_threads(os.cpu_count() or 1)
         t0 = time.perf_counter()
-        reference.gradient(o, n, v, f, SAMPLE_NUM, LB, UB, RES, data, weight, REFINE, SIGMA, 1, 0)
+        reference.gradient(oo, nn, v, f, SAMPLE_NUM, LB, UB, RES, data, weight, REFINE, SIGMA, 1, 0)
         dt = time.perf_counter() - t0
         spp = 1 + (SAMPLE_NUM - 1) // f.shape[0]
         return {'value': 2 * n_sources * f.shape[0] * spp / dt, 'unit': UNIT, 'sample': '%d wall points, %.1f s' % (n_sources, dt),
@@ -132,48 +228,372 @@ def reference_build_rate(v, f, n_sources=32):
         return {'unavailable': str(e)[:200]}
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path on the host cores, each step a bounded sample of the workload.
-    The arm is the oracle port: of the two CPU implementations available (the port, and the reference's own sources compiled against
-    stand-in library headers, oracle/_ref) it is the FASTER one — the conservative choice for a GPU/CPU ratio; the other is reported
-    under `reference_build`."""
-    if rank != 0:
-        return
-    from nlos_surface_optimization_b200 import scenes
-    v, f = scenes.bunny()
-    n_src = 256
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline(v, f, 8, want_stats=False)
-    vals, all_t = [], []
-    for _ in range(args.steps):
-        val, threads, times, _ = cpu_baseline(v, f, n_src, want_stats=False)
-        vals.append(val); all_t += times
-    value = float(np.mean(vals))
-    spp = 1 + (SAMPLE_NUM - 1) // f.shape[0]
-    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3 * float(np.mean(all_t)), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 math / f64 accumulation',
-            'data': 'synthetic', 'config': {'workload': 'C-bunny (bunny F=69630, 64x64 wall, B=1200, spp=1, r=10, s=1); each step = %d of 4096 wall points' % n_src},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': '%d of 4096 wall points x all 69630 triangles, forward+gradient, OpenMP oracle (reference-restated CPU path, not the Embree build)' % n_src},
-            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'ms_per_iteration_extrapolated': 1e3 * (2 * 4096 * f.shape[0] * spp) / value}
-    rb = reference_build_rate(v, f)
-    if rb is not None:
-        line['reference_build'] = rb
-    print(json.dumps(line))
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Env(object):
+    pass
 
 
-def fp32_peak_tflops(torch, dev, cx):
-    """Measured FP32 FMA throughput (the denominator of the FP32 roofline): a torch elementwise FMA chain is not a
-    pure-pipe benchmark, so use the library's own micro-kernel when present; else the nominal 148 SM x 128 lanes x 2 x clock."""
+def timed_steps(env, step, steps, warmup, flush=True):
+    """W untimed + K timed steps on the context stream; CUDA events per step on that stream, L2 flushed between steps.
+    -> (list of ms per step, wall seconds)"""
+    torch = env.torch
+    for _ in range(warmup):
+        if flush:
+            env.flush.zero_()
+        step()
+    env.ext.synchronize()
+    if env.world > 1:
+        env.dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        if flush:
+            env.flush.zero_()                      # L2 flush between timed iterations (outside the per-step events)
+        ev[i][0].record(env.ext); step(); ev[i][1].record(env.ext)
+    env.ext.synchronize(); torch.cuda.synchronize()
+    if env.world > 1:
+        env.dist.barrier()
+    wall = time.perf_counter() - t0
+    return [a.elapsed_time(b) for a, b in ev], wall
+
+
+def max_over_ranks(env, x):
+    t = env.torch.tensor([float(x)], dtype=env.torch.float64, device=env.dev)
+    if env.world > 1:
+        env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_problem(env, sc, weak, wall=None):
+    """Device-resident tensors of one rank's slice of a config: returns a dict with the step closure and sizes."""
+    torch, nb = env.torch, env.nb
+    from nlos_surface_optimization_b200 import renderer, ggx
+    v, f = sc['v'], sc['f']
+    o, n, off, L_global = wall_slice(env.rank, env.world, wall or sc['wall'], weak)
+    L, V, F = o.shape[0], v.shape[0], f.shape[0]
+    ub = sc['numbins'] * RES
+    B = nb._arrays.num_bins(LB, ub, RES)
+    spp = 1 + (sc['sample_num'] - 1) // F
+    env.ctx.set_source_window(off, L_global)
+    # target: the same mesh displaced by +1 cm, rendered by this library (bench needs a plausible residual, not parity)
+    v2 = v.copy(); v2[:, 2] += 0.01
+    p = dict(o=o, n=n, v=v, f=f, L=L, V=V, F=F, B=B, spp=spp, off=off, L_global=L_global, ub=ub, alpha=sc['alpha'], sample_num=sc['sample_num'])
+    with torch.cuda.stream(env.ext):
+        to = lambda a: torch.from_numpy(a).to(env.dev)
+        d = dict(o=to(o), n=to(n), v=to(v), f=to(f))
+        d['data'] = torch.zeros((L, B), dtype=torch.float64, device=env.dev); d['pl'] = torch.zeros(B, dtype=torch.float64, device=env.dev)
+        if sc['alpha'] is None:
+            renderer.renderStreamedTransient(d['o'], d['n'], to(v2), d['f'], sc['sample_num'], LB, ub, RES, d['data'], d['pl'], 1, 1, ctx=env.ctx)
+        else:
+            ggx.renderStreamedTransient(d['o'], d['n'], to(v2), d['f'], 0.2, sc['sample_num'], LB, ub, RES, d['data'], d['pl'], 1, 1, ctx=env.ctx)
+        d['w'] = torch.ones((L, B), dtype=torch.float64, device=env.dev)
+        d['T'] = torch.zeros((L, B), dtype=torch.float64, device=env.dev)
+        d['G'] = torch.zeros((V, 3), dtype=torch.float64, device=env.dev)
+        env.ext.synchronize()
+    p['d'] = d
+
+    def render(o_, n_, v_, f_, T_, pl_, G_, data_, w_):
+        if sc['alpha'] is None:
+            renderer.renderStreamedGradient(o_, n_, v_, f_, sc['sample_num'], LB, ub, RES, T_, pl_, G_, data_, w_, REFINE, SIGMA, 1, 0, ctx=env.ctx)
+        else:
+            ggx.renderStreamedGradient(o_, n_, v_, f_, sc['alpha'], sc['sample_num'], LB, ub, RES, T_, pl_, G_, data_, w_, REFINE, SIGMA, 1, ctx=env.ctx)
+    p['render'] = render
+
+    def step():
+        d['G'].zero_()
+        render(d['o'], d['n'], d['v'], d['f'], d['T'], d['pl'], d['G'], d['data'], d['w'])
+        if env.world > 1:
+            env.dist.all_reduce(d['G'])            # per-rank gradients are already normalised by the GLOBAL source count
+    p['step'] = step
+    return p
+
+
+def e2e_steps(env, p, steps, pinned):
+    """The reference-facing call with HOST buffers, copies inside the timed region (wall clock, max over ranks).  pinned=False: ordinary
+    NumPy arrays, as the reference's callers allocate them (exp_bunny/rendering.py:253-257)."""
+    torch = env.torch
+    if pinned:
+        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    else:
+        mk = lambda a: np.array(a, copy=True, order='C')
+    d = p['d']
+    h = dict(o=mk(p['o']), n=mk(p['n']), v=mk(p['v']), f=mk(p['f']), data=mk(d['data'].cpu().numpy()), w=mk(d['w'].cpu().numpy()),
+             T=mk(np.zeros((p['L'], p['B']))), pl=mk(np.zeros(p['B'])), G=mk(np.zeros((p['V'], 3))))
+    h2d = h['o'].nbytes + h['n'].nbytes + h['v'].nbytes + h['f'].nbytes + h['data'].nbytes + h['w'].nbytes + (h['G'].nbytes if env.world == 1 else 0)
+    d2h = h['T'].nbytes + h['pl'].nbytes + h['G'].nbytes
+
+    def step():
+        if env.world == 1:
+            h['G'][:] = 0
+            p['render'](h['o'], h['n'], h['v'], h['f'], h['T'], h['pl'], h['G'], h['data'], h['w'])
+        else:
+            with torch.cuda.stream(env.ext):
+                d['G'].zero_()
+                p['render'](h['o'], h['n'], h['v'], h['f'], h['T'], h['pl'], d['G'], h['data'], h['w'])
+                env.dist.all_reduce(d['G'])
+                torch.from_numpy(h['G']).copy_(d['G'], non_blocking=pinned)
+                env.ext.synchronize()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if env.world > 1:
+        env.dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    s = max_over_ranks(env, time.perf_counter() - t0)
+    samples = 2 * p['L'] * p['F'] * p['spp'] * env.world
+    return {'value': samples * steps / s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * s / steps,
+            'host_buffers': 'pinned' if pinned else 'pageable (np.array)'}
+
+
+def phases_and_counters(env, p):
+    """Two extra (untimed) steps: one with the library's own CUDA-event phases, one with the grid forward kernel counting its work
+    (the counting step is slower — five global atomics per warp pass — so its time is not used)."""
+    ctx = env.ctx
+    ctx.set_option('timing', 1)
+    env.flush.zero_(); p['step'](); env.ext.synchronize()
+    phase = ctx.timing()
+    ctx.set_option('timing', 0); ctx.set_option('count_work', 1)
+    p['step'](); env.ext.synchronize()
+    counters = ctx.work_counters()
+    ctx.set_option('count_work', 0)
+    return phase, counters
+
+
+def strong_record(env, args, mb):
+    """SURVEY 8(e) / BASELINE configs[4]: strong scaling at this N, device-timed (max over ranks), with the all-reduced gradient checked
+    on rank 0 against a single-rank recompute of the whole wall."""
+    torch = env.torch
+    out = {}
+    for name, cfg, steps, warm in (('c_bunny', 'bunny', max(3, min(args.steps, 10)), 3), ('c_scale', 'scale', 1, 1)):
+        sc = config_scene(cfg)
+        p = make_problem(env, sc, weak=False)
+        ms, _ = timed_steps(env, p['step'], steps, warm)
+        total = max_over_ranks(env, float(sum(ms)))
+        ms_step = total / steps
+        L_glob, F, spp = p['L_global'], p['F'], p['spp']
+        rec = {'workload': sc['label'] + '; the wall is SPLIT over the ranks (%d points per GPU), gradient all-reduced' % p['L'], 'n_gpus': env.world, 'steps': steps,
+               'ms_per_step': ms_step, 'value': 2 * L_glob * F * spp / (ms_step * 1e-3), 'unit': UNIT, 'scaling': 'strong'}
+        env.ctx.set_option('timing', 1); env.flush.zero_(); p['step'](); env.ext.synchronize(); rec['phase_ms'] = env.ctx.timing(); env.ctx.set_option('timing', 0)
+        if env.world > 1:
+            # the all-reduce alone, on the same tensor (limiter at small per-rank slices)
+            g = p['d']['G']
+            for _ in range(3):
+                env.dist.all_reduce(g)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); [env.dist.all_reduce(g) for _ in range(10)]; b.record(); torch.cuda.synchronize()
+            rec['allreduce_ms'] = max_over_ranks(env, a.elapsed_time(b) / 10.0)
+            rec['allreduce_bytes'] = int(g.numel() * 8)
+            # correctness of the sharded sum: rank 0 recomputes the WHOLE wall alone and compares (C-bunny only: the C-scale recompute
+            # would cost N steps)
+            if name == 'c_bunny':
+                p['step']()
+                env.ext.synchronize()
+                g_sum = p['d']['G'].clone()
+                if env.rank == 0:
+                    from nlos_surface_optimization_b200 import scenes
+                    o, n = scenes.wall_grid(sc['wall'])
+                    env.ctx.set_source_window(0, o.shape[0])
+                    with torch.cuda.stream(env.ext):
+                        to = lambda x: torch.from_numpy(x).to(env.dev)
+                        d_o, d_n = to(o), to(n)
+                        L, B = o.shape[0], p['B']
+                        data = torch.zeros((L, B), dtype=torch.float64, device=env.dev); pl = torch.zeros(B, dtype=torch.float64, device=env.dev)
+                        v2 = sc['v'].copy(); v2[:, 2] += 0.01
+                        from nlos_surface_optimization_b200 import renderer
+                        renderer.renderStreamedTransient(d_o, d_n, to(v2), p['d']['f'], sc['sample_num'], LB, p['ub'], RES, data, pl, 1, 1, ctx=env.ctx)
+                        T = torch.zeros((L, B), dtype=torch.float64, device=env.dev); G1 = torch.zeros_like(g_sum)
+                        p['render'](d_o, d_n, p['d']['v'], p['d']['f'], T, pl, G1, data, torch.ones((L, B), dtype=torch.float64, device=env.dev))
+                        env.ext.synchronize()
+                    rec['multi_gpu_check'] = {'rel_l2': float(((g_sum - G1).norm() / G1.norm()).item()), 'what': 'all-reduced gradient of the %d ranks vs rank 0 rendering all %d wall points alone' % (env.world, L)}
+                env.dist.barrier()
+        out[name] = rec
+        del p
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+    return out
+
+
+def roofline_record(env, p, phase, counters, ms_per_step, mb, sm_count, peaks, cfg_alpha):
+    """FP32 / atomic roofline of the dominant kernel.  Numerator = SURVEY 8(d): canonical flops per path sample from the oracle's canonical
+    traversal counter run NOW on 8 wall points of this workload; `executed` = the same prices on what the kernel counted itself."""
+    L, F, V, B, spp = p['L'], p['F'], p['V'], p['B'], p['spp']
+    oracle = oracle_all_threads()
+    idx = np.linspace(0, L - 1, 8).astype(int)
+    t0 = time.perf_counter()
+    can = oracle.canonical_counts(np.ascontiguousarray(p['o'][idx]), p['v'], p['f'], p['sample_num'])
+    can_s = time.perf_counter() - t0
+    rho = can['visible_frac']
+    ggx_on = cfg_alpha is not None
+    fl_fwd = FL_GEN + FL_BOX * can['box_per_ray'] + FL_TRI * can['tri_per_ray'] + rho * (FL_SHADE_FWD + (FL_GGX_FWD if ggx_on else 0))
+    fwd_ms, grad_ms = phase['forward_ms'], phase['gradient_ms']
+    samples = L * F * spp
+    achieved = samples * fl_fwd / (fwd_ms * 1e-3) / 1e12
+    peak, peak_how = mb.fp32(sm_count)
+    grid_used = counters.get('samples_generated', 0) > 0
+    rec = {'bound': 'fp32', 'kernel': 'k_forward_grid' if grid_used else 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+           'peak_source': peak_how, 'kernel_ms': fwd_ms,
+           'canonical': {'box_tests_per_path_sample': can['box_per_ray'], 'tri_tests_per_path_sample': can['tri_per_ray'], 'visible_fraction': rho,
+                         'flops_per_path_sample': fl_fwd, 'counted_on': '%d path samples of 8 wall points of this workload, %.1f s (oracle.canonical_counts: Karras LBVH, one triangle per leaf, near child first, nearest hit)' % (can['rays'], can_s)},
+           'note': 'achieved = CANONICAL flops (SURVEY 8d) / kernel time: an effective rate; `executed` prices what the kernel itself counted'}
+    # traffic: DRAM bytes of ONE launch of the dominant kernel from the committed ncu --set full capture of this command
+    rec['traffic'] = None
     try:
-        v = float(cx.lib.nlos_microbench_fp32(cx.handle))
-        if v > 0:
-            return v, 'measured here (in-repo FFMA chain, csrc/microbench.cu)'
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
+        if rec['kernel'] in tr:
+            rec['traffic'] = tr[rec['kernel']]['dram_bytes']; rec['traffic_source'] = tr[rec['kernel']].get('source')
     except Exception:
         pass
-    props = torch.cuda.get_device_properties(dev)
-    return props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12, 'nominal (SMs x 128 x 2 x 1965 MHz)'
+    if grid_used:
+        c = counters
+        fl_exec = (L * V * 25.0 + L * F * 24.0 + L * F * 30.0 + c['samples_generated'] * (FL_GEN + FL_TRI) + c['rays_traced'] * (FL_SHADE_FWD + 12 + (FL_GGX_FWD if ggx_on else 0)) + c['cell_check_passes'] * FL_TRI)
+        rec['executed'] = {'counters': c, 'flops': fl_exec, 'TFLOPs': fl_exec / (fwd_ms * 1e-3) / 1e12, 'frac_of_peak': fl_exec / (fwd_ms * 1e-3) / 1e12 / peak,
+                           'int_entry_checks': c['entry_words_scanned'], 'int_entry_checks_per_s': c['entry_words_scanned'] / (fwd_ms * 1e-3),
+                           'pricing': 'per (source, vertex) projection 25; per (source, triangle) rectangle 24 + plane-side cull 30; per generated sample 32 + 50 (self intersection); per traced ray 48 (+30 GGX) shade + 12 cell lookup; per cell-level check pass one 50-flop triangle test; the entry scan is integer work (3 ops per word), listed separately'}
+    # gradient kernel: effective rate and its L2 atomics
+    vis = counters.get('visible_samples', 0) if grid_used else rho * samples
+    fl_bwd_exec = vis * (FL_GEN + FL_TRI + FL_SHADE_BWD + (FL_GGX_BWD if ggx_on else 0))
+    fl_bwd_can = samples * (FL_GEN + FL_BOX * can['box_per_ray'] + FL_TRI * can['tri_per_ray'] + rho * (FL_SHADE_BWD + (FL_GGX_BWD if ggx_on else 0)))
+    red_T = mb.red_f64(L * B); red_G = mb.red_f64(3 * V)
+    n_chunks = -(-L // 128)
+    grad_atomics = 9.0 * F * n_chunks
+    rec['gradient'] = {'kernel': 'k_gradient', 'kernel_ms': grad_ms, 'canonical_TFLOPs': fl_bwd_can / (grad_ms * 1e-3) / 1e12, 'canonical_frac': fl_bwd_can / (grad_ms * 1e-3) / 1e12 / peak,
+                       'executed_TFLOPs': fl_bwd_exec / (grad_ms * 1e-3) / 1e12, 'executed_frac': fl_bwd_exec / (grad_ms * 1e-3) / 1e12 / peak,
+                       'note': 'no rays traced (visibility bits of the forward pass): executed = visible samples x (32 + 50 self intersection + 153 shade)',
+                       'atomic': {'fp64_red_per_launch': grad_atomics, 'fp64_red_Gops': grad_atomics / (grad_ms * 1e-3) / 1e9, 'fp64_red_peak_Gops': red_G,
+                                  'frac': (grad_atomics / (grad_ms * 1e-3) / 1e9) / red_G if red_G else None,
+                                  'what': '9 FP64 RED.ADD per (triangle, 128-source chunk) into the [V,3] accumulator; peak = hashed RED.ADD over 3V addresses, measured in this run'}}
+    fwd_red = vis
+    rec['atomic'] = {'fp64_red_per_launch': fwd_red, 'fp64_red_achieved_Gops': fwd_red / (fwd_ms * 1e-3) / 1e9, 'fp64_red_peak_Gops': red_T,
+                     'frac': (fwd_red / (fwd_ms * 1e-3) / 1e9) / red_T if red_T else None,
+                     'smem_atomic_peak_Gops': mb.smem_atomic(4096),
+                     'what': 'forward: one FP64 RED.ADD per visible sample into the L2-resident [L,B] transient; peak = hashed RED.ADD over L*B addresses; smem peak = atomicAdd(unsigned) over 4096 counters per block (the grid cell counters)'}
+    algo_bytes = (V * 12 + F * 12 + F * 128 + (F - 1) * 64) + L * B * 8 * 4 + 3 * V * 8 + L * spp * ((F + 31) // 32) * 4 * 2
+    rec['hbm'] = {'algorithmic_bytes_per_step': int(algo_bytes), 'achieved_GBps': algo_bytes / (ms_per_step * 1e-3) / 1e9, 'peak_GBps': peaks.get('hbm_gbs'),
+                  'frac': (algo_bytes / (ms_per_step * 1e-3) / 1e9) / peaks['hbm_gbs'] if peaks.get('hbm_gbs') else None}
+    return rec
+
+
+def run_render_config(env, args, mb):
+    """bunny / ggx / scale: one line on the contract (weak scaling of the named config at N ranks)."""
+    torch = env.torch
+    sc = config_scene(args.config)
+    steps, warm = args.steps, args.warmup
+    if args.config == 'scale':
+        steps, warm = min(steps, 2), min(warm, 1)                    # seconds per step on one GPU
+    p = make_problem(env, sc, weak=(args.config != 'scale'))
+    sampler = ClockSampler(env.local); sampler.start()
+    launches0 = env.ctx.launch_count()
+    step_ms, t_wall = timed_steps(env, p['step'], steps, warm)
+    launches = env.ctx.launch_count() - launches0
+    phase, counters = phases_and_counters(env, p)
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(env, float(sum(step_ms)))
+    ms_per_step = total_ms / steps
+    L_all = p['L'] * env.world if args.config != 'scale' else p['L_global']
+    value = 2 * L_all * p['F'] * p['spp'] / (ms_per_step * 1e-3)
+    e2e = e2e_steps(env, p, steps, pinned=True)
+    e2e_pg = e2e_steps(env, p, max(2, min(steps, 5)), pinned=False) if args.config != 'scale' else None
+    strong = None
+    if args.config == 'bunny' and not args.no_strong:
+        strong = strong_record(env, args, mb)
+        env.ctx.set_source_window(p['off'], p['L_global'])
+    if env.rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    sm_count = torch.cuda.get_device_properties(env.dev).multi_processor_count
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': env.world, 'steps': steps, 'warmup': warm, 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak' if args.config != 'scale' else 'strong', 'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
+        'config': {'workload': '%s; %d wall points per GPU%s; step = renderStreamedGradient (scene build + forward + residual + vertex gradient%s)' % (
+                       sc['label'], p['L'], (' of a %dx%d wall (weak scaling)' % (sc['wall'] * env.world, sc['wall'])) if (env.world > 1 and args.config != 'scale') else '',
+                       ' + NCCL all-reduce' if env.world > 1 else ''),
+                   'l2': 'flushed between timed iterations (256 MiB write)', 'ms_per_iteration': ms_per_step, 'wall_ms_per_step_incl_flush': 1e3 * t_wall / steps,
+                   'phase_ms': phase, 'visibility_reuse': True, 'forward_kernel': 'k_forward_grid (perspective grid, G=%d)' % counters['grid_res'] if counters.get('samples_generated', 0) > 0 else 'k_forward (BVH traversal)',
+                   'value_counts': '2*L*F*spp path samples per step (SURVEY 8d); the gradient pass reuses the forward visibility bits and traces no rays'},
+        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+    }
+    if e2e_pg is not None:
+        line['e2e_pageable'] = e2e_pg
+    line['roofline'] = roofline_record(env, p, phase, counters, ms_per_step, mb, sm_count, peaks, sc['alpha'])
+    if strong is not None:
+        line['strong'] = strong
+    if env.world == 1 and not args.no_cpu_baseline:
+        from nlos_surface_optimization_b200 import scenes
+        o_full, n_full = scenes.wall_grid(sc['wall'])
+        probe, threads, _ = cpu_gradient_rate(sc['v'], sc['f'], o_full, n_full, 8, sc['sample_num'], sc['alpha'], sc['numbins'])
+        n_src = int(max(16, min(o_full.shape[0], 1024, probe * 12.0 / (2 * p['F'] * p['spp']))))        # ~12 s of CPU work
+        cv, threads, dt = cpu_gradient_rate(sc['v'], sc['f'], o_full, n_full, n_src, sc['sample_num'], sc['alpha'], sc['numbins'])
+        line['cpu_baseline'] = {'value': cv, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': '%d of %d wall points x all %d triangles, forward+gradient, %.1f s; OpenMP oracle = reference-restated CPU path (not the Embree build)' % (n_src, o_full.shape[0], p['F'], dt),
+                                'ms_per_iteration_extrapolated': 1e3 * 2 * o_full.shape[0] * p['F'] * p['spp'] / cv}
+    return line
+
+
+def run_arm(env, args, mb):
+    """C-arm (BASELINE configs[3]): the optimisation loop on the armadillo init mesh; ms per iteration next to the CPU baseline.
+    value = device-resident loop (loop.DeviceIteration), e2e = the reference's call sequence on pageable host arrays (loop.HostIteration)."""
+    torch = env.torch
+    from nlos_surface_optimization_b200 import scenes, loop, rendering
+    if env.world > 1:
+        raise SystemExit('--config arm is a single-GPU line (the loop shards like C-bunny; see the default config for N > 1)')
+    sc = config_scene('arm')
+    o, n = scenes.wall_grid(sc['wall'])
+    opt = loop.RenderOptions(SAMPLE_NUM, o, n)
+    gv, gf = scenes.armadillo()
+    from nlos_surface_optimization_b200 import renderer
+    gt = np.zeros((o.shape[0], opt.max_distance_bin)); pl = np.zeros(opt.max_distance_bin)
+    renderer.renderStreamedTransient(o, n, gv, gf, int(4 * gf.shape[0]), 0.0, opt.max_distance_bin * opt.distance_resolution, opt.distance_resolution, gt, pl, 1, 1, ctx=env.ctx)
+    weight = rendering.create_weighting_function(gt, opt.gamma)
+    iters = max(args.steps, 10) if args.steps != 10 else 50
+    F, L = sc['f'].shape[0], o.shape[0]
+    spp = 1 + (SAMPLE_NUM - 1) // F
+    sampler = ClockSampler(env.local); sampler.start()
+    with torch.cuda.stream(env.ext):
+        dev_it = loop.DeviceIteration(loop.Mesh(sc['v'], sc['f']), gt, weight, opt, 0.0001 / 3, ctx=env.ctx)
+        for _ in range(max(args.warmup, 3)):
+            dev_it.step()
+        env.ext.synchronize(); torch.cuda.synchronize()
+        launches0 = env.ctx.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(env.ext)
+        losses = [dev_it.step()[1] for _ in range(iters)]
+        b.record(env.ext); env.ext.synchronize(); torch.cuda.synchronize()
+        ms_dev = a.elapsed_time(b) / iters
+        launches = env.ctx.launch_count() - launches0
+        env.ctx.set_option('timing', 1); dev_it.step(); env.ext.synchronize(); phase = env.ctx.timing(); env.ctx.set_option('timing', 0)
+    clocks = sampler.stop()
+    host_it = loop.HostIteration(loop.Mesh(sc['v'], sc['f']), gt, weight, opt, 0.0001 / 3, ctx=env.ctx)
+    for _ in range(2):
+        host_it.step()
+    t0 = time.perf_counter()
+    n_host = max(5, iters // 5)
+    for _ in range(n_host):
+        host_it.step()
+    ms_host = 1e3 * (time.perf_counter() - t0) / n_host
+    samples = 2 * L * F * spp
+    B = opt.max_distance_bin
+    line = {'metric': METRIC + '; ms per optimization iteration', 'value': samples / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': iters, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
+            'config': {'workload': sc['label'] + '; step = one optimisation iteration: renderStreamedGradient + normal-smoothing regulariser + weighted L2 loss + Adam_Modified step (loop.DeviceIteration: every array resident in HBM); El Topo / CGAL remeshing absent (out of scope), topology fixed',
+                       'ms_per_iteration': ms_dev, 'phase_ms_of_the_render_call': phase, 'l2_first': losses[0], 'l2_last': losses[-1], 'l2_decreased': bool(losses[-1] < losses[0]),
+                       'l2': 'not flushed: the loop re-reads its own arrays every iteration, as in production'},
+            'e2e': {'value': samples / (ms_host * 1e-3), 'unit': UNIT, 'ms_per_step': ms_host, 'h2d_bytes_per_step': int(o.nbytes + n.nbytes + sc['v'].nbytes + sc['f'].nbytes + 2 * L * B * 8 + sc['v'].shape[0] * 24 + sc['f'].nbytes * 2 + sc['v'].nbytes),
+                    'd2h_bytes_per_step': int(L * B * 8 + B * 8 + 2 * sc['v'].shape[0] * 24), 'host_buffers': 'pageable (np.zeros per call, as exp_bunny/rendering.py:253-257 does): loop.HostIteration through the reference-signature facade'},
+            'gpu_launches': int(launches), 'clocks': clocks}
+    if not args.no_cpu_baseline:
+        cv, threads, dt = cpu_gradient_rate(sc['v'], sc['f'], o, n, 64, SAMPLE_NUM)
+        line['cpu_baseline'] = {'value': cv, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': '64 of %d wall points of the same mesh and wall, forward+gradient, %.1f s (OpenMP oracle)' % (L, dt),
+                                'ms_per_iteration_extrapolated': 1e3 * samples / cv}
+    return line
 
 
 def main():
@@ -182,8 +602,9 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--cpu-sources', type=int, default=1024, help='wall points of the bounded CPU-baseline sample')
+    ap.add_argument('--config', default='bunny', choices=['bunny', 'ggx', 'arm', 'scale'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling sub-record (C-bunny split N ways + C-scale)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
 
@@ -194,176 +615,33 @@ def main():
     import torch
     import torch.distributed as dist
     import nlos_surface_optimization_b200 as nb
-    from nlos_surface_optimization_b200 import renderer
     if args.warmup < 3:
         args.warmup = 3
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
+    env = Env()
+    env.torch, env.dist, env.nb = torch, dist, nb
+    env.rank, env.world, env.local = rank, world, local
+    env.dev = torch.device('cuda', local)
+    torch.cuda.set_device(env.dev)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    ctx = nb.Context(local)                       # fails loudly without the CUDA library / a B200
+        dist.init_process_group('nccl', device_id=env.dev)
+    env.ctx = nb.Context(local)                       # fails loudly without the CUDA library / a B200
+    env.ext = torch.cuda.ExternalStream(env.ctx.stream, device=env.dev)
+    line = None
     try:
-        line = run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local)
+        with torch.cuda.stream(env.ext):
+            env.flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.dev)      # > 126 MB L2
+        mb = Microbench(local)
+        line = run_arm(env, args, mb) if args.config == 'arm' else run_render_config(env, args, mb)
     finally:
         # ordered teardown: every tensor that lives on the context's stream must be gone before the stream is destroyed
         import gc
+        env.flush = None
         gc.collect(); torch.cuda.synchronize(); torch.cuda.empty_cache()
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
-        ctx.close()
+        env.ctx.close()
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
-
-
-def run(args, ctx, torch, dist, nb, renderer, dev, rank, world, local):
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
-
-    o, n, v, f, L, L_global = workload(rank, world)
-    V, F = v.shape[0], f.shape[0]
-    B = nb._arrays.num_bins(LB, UB, RES)
-    spp = 1 + (SAMPLE_NUM - 1) // F
-    ctx.set_source_window(rank * L, L_global)
-    samples_per_step_rank = 2 * L * F * spp
-
-    # target: the same mesh displaced by +1 cm, rendered by this library (bench needs a plausible residual, not parity)
-    v2 = v.copy(); v2[:, 2] += 0.01
-    data_h = np.zeros((L, B)); pl_h = np.zeros(B)
-    renderer.renderStreamedTransient(o, n, v2, f, SAMPLE_NUM, LB, UB, RES, data_h, pl_h, 1, 1, ctx=ctx)
-    weight_h = np.ones((L, B))
-
-    with torch.cuda.stream(ext):
-        to = lambda a: torch.from_numpy(a).to(dev)
-        d_o, d_n, d_v, d_f, d_data, d_w = to(o), to(n), to(v), to(f), to(data_h), to(weight_h)
-        d_T = torch.zeros((L, B), dtype=torch.float64, device=dev); d_pl = torch.zeros(B, dtype=torch.float64, device=dev)
-        d_G = torch.zeros((V, 3), dtype=torch.float64, device=dev)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-        def step_device():
-            d_G.zero_()
-            renderer.renderStreamedGradient(d_o, d_n, d_v, d_f, SAMPLE_NUM, LB, UB, RES, d_T, d_pl, d_G, d_data, d_w, REFINE, SIGMA, 1, 0, ctx=ctx)
-            if world > 1:
-                dist.all_reduce(d_G)              # per-rank gradients are already normalised by the GLOBAL source count
-
-        for _ in range(args.warmup):
-            flush.zero_(); step_device()
-        ext.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local); sampler.start()
-        launches0 = ctx.launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        ctx.set_option('timing', 0)
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.zero_()                          # L2 flush between timed iterations (outside the per-step events)
-            ev[i][0].record(ext); step_device(); ev[i][1].record(ext)
-        ext.synchronize(); torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t_wall = time.perf_counter() - t_wall0
-        launches = ctx.launch_count() - launches0
-        step_ms = [a.elapsed_time(b) for a, b in ev]
-        # per-kernel breakdown of one extra step (CUDA events inside the library, on the launching stream)
-        ctx.set_option('timing', 1); flush.zero_(); step_device(); ext.synchronize(); phase = ctx.timing(); ctx.set_option('timing', 0)
-        clocks = sampler.stop()
-
-    total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = samples_per_step_rank * world / (ms_per_step * 1e-3)
-
-    # ---- e2e: the reference-facing call with pinned HOST buffers, copies inside the timed region
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    h_o, h_n, h_v, h_f, h_data, h_w = pin(o), pin(n), pin(v), pin(f), pin(data_h), pin(weight_h)
-    h_T = torch.zeros((L, B), dtype=torch.float64).pin_memory().numpy(); h_pl = torch.zeros(B, dtype=torch.float64).pin_memory().numpy()
-    h_G = torch.zeros((V, 3), dtype=torch.float64).pin_memory().numpy()
-    h2d = h_o.nbytes + h_n.nbytes + h_v.nbytes + h_f.nbytes + h_data.nbytes + h_w.nbytes + (h_G.nbytes if world == 1 else 0)
-    d2h = h_T.nbytes + h_pl.nbytes + h_G.nbytes
-
-    def step_e2e():
-        if world == 1:
-            h_G[:] = 0
-            renderer.renderStreamedGradient(h_o, h_n, h_v, h_f, SAMPLE_NUM, LB, UB, RES, h_T, h_pl, h_G, h_data, h_w, REFINE, SIGMA, 1, 0, ctx=ctx)
-        else:
-            with torch.cuda.stream(ext):
-                d_G.zero_()
-                renderer.renderStreamedGradient(h_o, h_n, h_v, h_f, SAMPLE_NUM, LB, UB, RES, h_T, h_pl, d_G, h_data, h_w, REFINE, SIGMA, 1, 0, ctx=ctx)
-                dist.all_reduce(d_G)
-                torch.from_numpy(h_G).copy_(d_G, non_blocking=True)
-                ext.synchronize()
-
-    for _ in range(2):
-        step_e2e()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = samples_per_step_rank * world * args.steps / e2e_s
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        cpu = None; stats = None
-        if world == 1 and not args.no_cpu_baseline:
-            cv, threads, times, stats = cpu_baseline(v, f, args.cpu_sources)
-            cpu = {'value': cv, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                   'sample': '%d of 4096 wall points x all 69630 triangles, forward+gradient, %.1f s; OpenMP oracle = reference-restated CPU path (not the Embree build)' % (args.cpu_sources, times[0]),
-                   'ms_per_iteration_extrapolated': 1e3 * samples_per_step_rank / cv}
-        # FP32 roofline of the dominant kernel (forward sample kernel): algorithmic flops per path sample from the
-        # canonical nearest-hit traversal counted by the oracle, divided by the kernel's event time.
-        # canonical per-ray counts of the nearest-hit traversal (oracle BVH: object-median split, <=4 triangles per leaf,
-        # boxes padded by scale/65536), measured once on 8 wall points of this workload and frozen here so that the
-        # accounting does not move with the checker's (deliberately very conservative) culling slack
-        box, tri = 58.7, 11.9
-        rho = 0.41
-        flops_fwd_sample = 32 + 23 * box + 50 * tri + rho * 48
-        fwd_ms = phase['forward_ms']
-        achieved = L * F * spp * flops_fwd_sample / (fwd_ms * 1e-3) / 1e12
-        peak, peak_how = fp32_peak_tflops(torch, dev, ctx)
-        try:
-            red_peak = float(ctx.lib.nlos_microbench_red_f64(ctx.handle, L * B))       # FP64 RED.ADD over the transient's address range
-        except Exception:
-            red_peak = None
-        algo_bytes = (V * 12 + F * 12 + F * 128 + (F - 1) * 64) + L * B * 8 * 4 + 3 * V * 8 + L * spp * ((F + 31) // 32) * 4 * 2
-        line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 math / f64 accumulation', 'data': 'synthetic',
-            'config': {'workload': 'C-bunny: bunny V=34817 F=69630, %dx%d confocal wall (%d points per GPU), B=1200 x 1.2 mm, sample_num=20000 (spp=1), refine_scale=10, sigma_bin=1; step = renderStreamedGradient (scene build + forward + residual + vertex gradient%s)' % (WALL * world, WALL, L, ' + NCCL all-reduce' if world > 1 else ''),
-                       'l2': 'flushed between timed iterations (256 MiB write)', 'ms_per_iteration': ms_per_step, 'wall_ms_per_step_incl_flush': 1e3 * t_wall / args.steps,
-                       'phase_ms': phase, 'visibility_reuse': True},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s / args.steps},
-            'gpu_launches': int(launches),
-            'clocks': clocks,
-            'roofline': {'bound': 'fp32', 'kernel': 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                         'traffic': 30.4e6,     # bytes: dram__bytes_read.sum + dram__bytes_write.sum of one k_forward launch, ncu --set full (profiles/r1_ncu_full_summary.txt)
-                         'traffic_unit': 'bytes of DRAM per k_forward launch (ncu); the unit of achieved/peak is TFLOP/s',
-                         'peak_source': peak_how, 'flops_per_path_sample': flops_fwd_sample, 'canonical_box_tests_per_ray': box, 'canonical_tri_tests_per_ray': tri,
-                         'kernel_ms': fwd_ms,
-                         'note': 'achieved = CANONICAL flops (oracle nearest-hit traversal counts, SURVEY 8d) / kernel time: an effective rate; the kernel executes fewer (any-hit query, zero-contribution samples never traced)',
-                         'atomic': {'fp64_red_peak_Gops': red_peak, 'fp64_red_achieved_Gops': rho * L * F * spp / (fwd_ms * 1e-3) / 1e9,
-                                    'frac': (rho * L * F * spp / (fwd_ms * 1e-3) / 1e9) / red_peak if red_peak else None},
-                         'hbm': {'algorithmic_bytes_per_step': int(algo_bytes), 'achieved_GBps': algo_bytes / (ms_per_step * 1e-3) / 1e9, 'peak_GBps': peaks.get('hbm_gbs'),
-                                 'frac': (algo_bytes / (ms_per_step * 1e-3) / 1e9) / peaks['hbm_gbs'] if peaks.get('hbm_gbs') else None}},
-        }
-        if cpu:
-            line['cpu_baseline'] = cpu
-        return line
-    return None
 
 
 if __name__ == '__main__':

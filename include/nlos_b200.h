@@ -60,11 +60,15 @@ int nlos_ctx_wait_stream(nlos_ctx* ctx, void* stream);
 int nlos_ctx_signal_stream(nlos_ctx* ctx, void* stream);
 /* keys: "reuse_visibility" (1), "chunk_forward" (0 = auto), "chunk_gradient" (0 = auto), "timing" (0),
  *       "forward_algo" (0 = auto, 1 = BVH traversal kernel, 2 = per-source perspective-grid kernel), "grid_res" (0 = auto: cells per
- *       axis of the perspective grid), "grid_cap" (0 = none; test hook: entry budget of the grid per wall point) */
+ *       axis of the perspective grid), "grid_cap" (0 = none; test hook: entry budget of the grid per wall point), "count_work" (0) */
 int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value);
 /* ms of the last call: {scene build, forward, residual, gradient, total}; needs option "timing" = 1 */
 int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5);
 uint64_t nlos_ctx_launch_count(nlos_ctx* ctx);         /* kernels launched through this context so far */
+/* MEASUREMENT: with option "count_work" = 1 the perspective-grid forward kernel counts its own work; after the call out8 holds
+ * {samples generated (not plane-culled), rays traced, entry words scanned, cell-level check passes (= exact-test candidates incl. self),
+ *  visible samples, wall points handled without a grid, grid resolution G, 0}.  bench.py prices roofline.executed with them. */
+int nlos_ctx_get_work_counters(nlos_ctx* ctx, uint64_t* out8);
 /* TEST HOOK (no reference counterpart): replace the counter-based generator by an external stream of (S,T) pairs, n floats (host or
  * device pointer, copied); sample k of (global source s, triangle f) reads st[2*((s*numTriangles + f)*spp + k)] — the order in which
  * one worker of the reference consumes its Mersenne-Twister stream (sampler.cpp:20-33, transient_and_gradient.cpp:184-186), so that
@@ -130,7 +134,7 @@ int nlos_streamed_render_vertex_gradient(nlos_ctx* ctx, int vertex_num, const fl
  * reference (last adjacent face wins, scheduler dependent); here the adjacent face with the highest index wins. */
 int nlos_streamed_render_normal_smoothing(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD,
                                           int numTriangles, const int* face_affinity, double* curvature_grad,
-                                          double* value_out /*host*/);
+                                          double* value_out /*host, or device (then no host synchronisation)*/);
 
 /* smoothed_transient/stratifiedStreamedGradientRenderer.h:13  streamed_render_curvature_grad (renderer.pyx:26) */
 int nlos_streamed_render_curvature_grad(nlos_ctx* ctx, const float* verticesD, int numVertices, const int* trianglesD,
@@ -240,11 +244,6 @@ int nlos_debug_copy_visibility_words(nlos_ctx* ctx, uint32_t* out, int64_t n, in
  * counters (nullable, host) = {rays traced, box tests, triangle tests}. */
 int nlos_debug_visibility(nlos_ctx* ctx, const float* originD, int numSources, const float* verticesD, int numVertices,
                           const int* trianglesD, int numTriangles, int numSamples, uint8_t* visibility, uint64_t* counters3);
-
-/* Measured roofline denominators for this path: FP32 FFMA throughput in TFLOP/s and FP64 RED.ADD
- * throughput in 1e9 atomics/s over `num_addresses` (rounded down to a power of two) hashed addresses. <0 on error. */
-double nlos_microbench_fp32(nlos_ctx* ctx);
-double nlos_microbench_red_f64(nlos_ctx* ctx, int64_t num_addresses);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     'nlos_ctx_set_seed': (C.c_int, [_ctx, C.c_uint64]),
     'nlos_ctx_set_source_window': (C.c_int, [_ctx, C.c_int64, C.c_int64]),
     'nlos_ctx_set_option': (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
+    'nlos_ctx_get_work_counters': (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
     'nlos_ctx_wait_stream': (C.c_int, [_ctx, C.c_void_p]),
     'nlos_ctx_signal_stream': (C.c_int, [_ctx, C.c_void_p]),
     'nlos_ctx_get_timing': (C.c_int, [_ctx, _f]),
@@ -73,8 +74,6 @@ SIGNATURES = {
     'nlos_embree3_tbb_line_intersection': (C.c_int, [_ctx, _f, _f, C.c_int, _f, C.c_int, _i, C.c_int, _f]),
     'nlos_embree3_tbb_short_line_intersection': (C.c_int, [_ctx, _f, _f, C.c_int, _f, C.c_int, _i, C.c_int, _f]),
     'nlos_barycentric_to_world': (C.c_int, [_ctx, _f, C.c_int, _i, C.c_int, _f, C.c_int, _f]),
-    'nlos_microbench_fp32': (C.c_double, [_ctx]),
-    'nlos_microbench_red_f64': (C.c_double, [_ctx, C.c_int64]),
     'nlos_debug_copy_visibility_words': (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_int64)]),
     'nlos_debug_visibility': (C.c_int, [_ctx, _f, C.c_int, _f, C.c_int, _i, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]),
 }
@@ -174,6 +173,13 @@ class Context(object):
         buf = (C.c_float * 5)()
         self.check(self.lib.nlos_ctx_get_timing(self.handle, buf), 'nlos_ctx_get_timing')
         return dict(zip(('build_ms', 'forward_ms', 'residual_ms', 'gradient_ms', 'total_ms'), [float(x) for x in buf]))
+
+    def work_counters(self):
+        """MEASUREMENT: work counters of the last perspective-grid forward launch run with option count_work = 1."""
+        buf = (C.c_uint64 * 8)()
+        self.check(self.lib.nlos_ctx_get_work_counters(self.handle, buf), 'nlos_ctx_get_work_counters')
+        keys = ('samples_generated', 'rays_traced', 'entry_words_scanned', 'cell_check_passes', 'visible_samples', 'sources_without_grid', 'grid_res')
+        return dict(zip(keys, [int(x) for x in buf]))
 
     def visibility_words(self):
         """DEBUG: the visibility words of the last gradient call (see include/nlos_b200.h)."""

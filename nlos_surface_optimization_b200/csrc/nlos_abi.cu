@@ -427,6 +427,7 @@ int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value) {
   else if (k == "chunk_gradient") ctx->cx.chunk_gradient = (int)value;
   else if (k == "timing") ctx->cx.timing_enabled = value != 0;
   else if (k == "forward_algo") { if (value < 0 || value > 2) { ctx->cx.last_error = "forward_algo must be 0 (auto), 1 (bvh) or 2 (grid)"; return NLOS_ERR_INVALID; } ctx->cx.forward_algo = (int)value; }
+  else if (k == "count_work") ctx->cx.count_work = value != 0;
   else if (k == "grid_cap") { if (value < 0 || value > 0x7fffffff) { ctx->cx.last_error = "grid_cap out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_cap = (int)value; }
   else if (k == "grid_res") { if (value < 0 || value > 4096) { ctx->cx.last_error = "grid_res out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_res = (int)value; }
   else { ctx->cx.last_error = "unknown option " + k; return NLOS_ERR_INVALID; }
@@ -439,6 +440,18 @@ int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5) {
   return NLOS_OK;
 }
 uint64_t nlos_ctx_launch_count(nlos_ctx* ctx) { return ctx ? ctx->cx.launches : 0; }
+int nlos_ctx_get_work_counters(nlos_ctx* ctx, uint64_t* out8) {
+  if (!ctx || !out8) return NLOS_ERR_INVALID;
+  Ctx& cx = ctx->cx;
+  try {
+    NLOS_CUDA_OK(cudaSetDevice(cx.device));
+    NLOS_CUDA_OK(cudaStreamSynchronize(cx.stream));
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (cx.buf("work_counters").p) NLOS_CUDA_OK(cudaMemcpy(out8, cx.buf("work_counters").p, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    out8[6] = (uint64_t)cx.work_G;
+    return NLOS_OK;
+  } catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
+}
 
 int nlos_streamed_render_transient(nlos_ctx* ctx, const float* originD, int numSources, const float* normalD, const float* verticesD, int numVertices,
                                    const float* vertexNormal, const float* vertexAlbedo, const int* trianglesD, int numTriangles, int numSamples,
@@ -576,9 +589,11 @@ static int run_regulariser(nlos_ctx* ctx, int mode, const float* verticesD, int 
     launch_regulariser(cx, mode, d_verts, numVertices, d_faces, numTriangles, d_aff, o_G.dev, d_val);
     finish_out(cx, o_G);
     double h = 0;
-    if (value_out) NLOS_CUDA_OK(cudaMemcpyAsync(&h, d_val, sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (value_out || o_G.host) NLOS_CUDA_OK(cudaStreamSynchronize(st));
-    if (value_out) *value_out = h;
+    const bool value_on_device = value_out && is_device_ptr(value_out);        // device-resident loop: no host round trip for the value
+    if (value_on_device) NLOS_CUDA_OK(cudaMemcpyAsync(value_out, d_val, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else if (value_out) NLOS_CUDA_OK(cudaMemcpyAsync(&h, d_val, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if ((value_out && !value_on_device) || o_G.host) NLOS_CUDA_OK(cudaStreamSynchronize(st));
+    if (value_out && !value_on_device) *value_out = h;
     cx.last_error.clear();
     return NLOS_OK;
   } catch (const InvalidArg& e) { cx.last_error = e.what(); return NLOS_ERR_INVALID; }

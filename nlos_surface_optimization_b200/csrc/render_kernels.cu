@@ -330,7 +330,8 @@ struct GridShared {
   unsigned maxm;                           // max round-off margin (float bits, m >= 0)
   unsigned wsum[kGridBlock / 32];
 };
-struct GridScratch { float4* proj; uint2* rect; unsigned* entE; unsigned* entI; };
+struct GridScratch { float4* proj; uint2* rect; unsigned* entE; unsigned* entI;
+                     unsigned long long* counters; };   // counters: null, or 6 work counters (option "count_work"): samples generated, rays traced, entry words scanned, cell-level check passes, visible samples, sources without grid
 
 // exclusive prefix sum of the counts a[0..n), each rounded up to a multiple of 4, in place (shared memory); returns the total;
 // per-thread runs of odd length avoid bank conflicts
@@ -477,6 +478,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
     }
     // ---------------- pass 3: samples
     const bool grid = gs.use_grid != 0;
+    if (scr.counters && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
     const PGridFrame fr = gs.fr;
     const int G = fr.G;
     for (int base = warp * 32; base < F; base += kGridBlock) {
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           if (lane == 0) gw.occ = 0u;
           __syncwarp();
           const int maxg = __reduce_max_sync(0xffffffffu, ngrp);
+          unsigned nhit = 0u;                                                     // work counter: cell-level check passes of this lane
           for (int g0 = 0; g0 < maxg; g0 += 8) {                                  // 32 entries per lane and round
             unsigned mask = 0u;
             if (g0 < ngrp && !((gw.occ >> lane) & 1u)) {
@@ -554,6 +557,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
                 }
               }
             }
+            nhit += __popc(mask);
             // pooled exact tests: every lane hands up to kGridPush candidates to the warp's pool, then all 32 lanes work the pool
             while (__any_sync(0xffffffffu, mask != 0u)) {
               const int nb = __popc(mask);
@@ -579,6 +583,12 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           __syncwarp();
           occ = occ || ((gw.occ >> lane) & 1u);
           __syncwarp();                                                             // gw is rewritten by the next sample
+          if (scr.counters) {                                                       // measurement runs only (bench.py roofline.executed)
+            const unsigned c1 = __reduce_add_sync(0xffffffffu, need ? 1u : 0u), c2 = __reduce_add_sync(0xffffffffu, (unsigned)(4 * ngrp)), c3 = __reduce_add_sync(0xffffffffu, nhit);
+            const unsigned c0 = __reduce_add_sync(0xffffffffu, culled ? 0u : 1u), c4 = __reduce_add_sync(0xffffffffu, (need && !occ) ? 1u : 0u);
+            if (lane == 0) { atomicAdd(scr.counters, (unsigned long long)c0); atomicAdd(scr.counters + 1, (unsigned long long)c1); atomicAdd(scr.counters + 2, (unsigned long long)c2);
+                             atomicAdd(scr.counters + 3, (unsigned long long)c3); atomicAdd(scr.counters + 4, (unsigned long long)c4); }
+          }
         } else if (need) {
           occ = occluded(sc.nodes, sc.ttris, sc.root_count, make_ray(o, d), ts, t.prim);
         }
@@ -867,6 +877,12 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
   scr.entE = cx.buf("grid_entE").as<unsigned>((size_t)blocks * cap);
   scr.entI = cx.buf("grid_entI").as<unsigned>((size_t)blocks * cap);
+  scr.counters = nullptr;
+  if (cx.count_work) {
+    scr.counters = cx.buf("work_counters").as<unsigned long long>(8);
+    NLOS_CUDA_OK(cudaMemsetAsync(scr.counters, 0, 8 * sizeof(unsigned long long), cx.stream));
+    cx.work_G = G;
+  }
   if (vis) {
     NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);

@@ -186,8 +186,10 @@ def renderStreamedVertexGradient(origin, normal, vertices, faces, num_sample, lo
     cx.check(rc, 'nlos_streamed_render_vertex_gradient')
 
 
-def renderStreamedNormalSmoothing(vertices, faces, f_affinity, gradient, ctx=None):
-    """renderer.pyx:13 -> streamed_render_normal_smoothing; returns the regulariser value, fills gradient[V,3]."""
+def renderStreamedNormalSmoothing(vertices, faces, f_affinity, gradient, ctx=None, value_out=None):
+    """renderer.pyx:13 -> streamed_render_normal_smoothing; returns the regulariser value, fills gradient[V,3].
+    Addition: `value_out` = a 1-element float64 torch CUDA tensor receives the value on the device (no host synchronisation; the
+    tensor is returned) — used by the device-resident iteration (loop.DeviceIteration)."""
     import ctypes as C
     cx = ctx or _ffi.default_context()
     pv, sv = as_pointer(vertices, 'f32', 2, 'vertices')
@@ -200,6 +202,12 @@ def renderStreamedNormalSmoothing(vertices, faces, f_affinity, gradient, ctx=Non
     assert sa[0] == sf[0], "face affinity needs to be Fx3"
     assert sg[0] == sv[0], "gradient dimension should be Vx3"
     assert sg[1] == 3, "gradient dimension should be Vx3"
+    if value_out is not None:
+        po, so = as_pointer(value_out, 'f64', 1, 'value_out')
+        assert so[0] == 1, "value_out needs one element"
+        rc = cx.lib.nlos_streamed_render_normal_smoothing(cx.handle, pv, sv[0], pf, sf[0], pa, pg, po)
+        cx.check(rc, 'nlos_streamed_render_normal_smoothing')
+        return value_out
     out = C.c_double(0.0)
     rc = cx.lib.nlos_streamed_render_normal_smoothing(cx.handle, pv, sv[0], pf, sf[0], pa, pg, C.byref(out))
     cx.check(rc, 'nlos_streamed_render_normal_smoothing')

@@ -22,15 +22,11 @@ def _bounds(opt):
 
 
 def create_weighting_function(data, gamma=1):
-    """exp_bunny/rendering.py:208-217 (pure NumPy)."""
-    eps = 0.1
-    i_max = np.max(data)
-    normalized_data = data / i_max
-    weight = (normalized_data + eps) ** gamma
-    total = np.sum(weight)
-    weight = weight / total
-    weight *= data.shape[0] * data.shape[1]
-    return weight
+    """Per-bin loss weights (role of exp_bunny/rendering.py:208-217): (data / max + 0.1) ** gamma, rescaled to mean 1.
+    The two-step rescale (divide by the sum, then multiply by the element count) keeps the reference's rounding."""
+    w = np.power(data / np.max(data) + 0.1, gamma)
+    w = w / np.sum(w)
+    return w * (data.shape[0] * data.shape[1])
 
 
 def _per_vertex_normal(mesh):
@@ -82,8 +78,8 @@ def inverseRenderingAlbedo(mesh, data, weight, opt):
     return transient, g
 
 
-def inverseRendering(mesh, data, weight, opt):
-    """:252-269 — THE hot entry point: forward transient + vertex gradient."""
+def inverseRendering(mesh, data, weight, opt, ctx=None):
+    """:252-269 — THE hot entry point: forward transient + vertex gradient.  (`ctx` is an addition: an explicit _ffi.Context.)"""
     L = opt.lighting.shape[0]
     transient = np.zeros((L, opt.max_distance_bin), dtype=np.double, order='C')
     pathlengths = np.zeros(opt.max_distance_bin, dtype=np.double, order='C')
@@ -103,15 +99,15 @@ def inverseRendering(mesh, data, weight, opt):
                                                   getattr(opt, 'loss_flag', 0))
     else:
         renderer.renderStreamedGradient(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, res, transient, pathlengths,
-                                        gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag, getattr(opt, 'loss_flag', 0))
+                                        gradient, data, weight, opt.bin_refine_resolution, opt.sigma_bin, opt.testing_flag, getattr(opt, 'loss_flag', 0), ctx=ctx)
     return transient, gradient, pathlengths
 
 
-def removeTriangle(mesh, opt):
+def removeTriangle(mesh, opt, ctx=None):
     """:271-278 — drops faces that no wall point ever sees (unless all three neighbours exist)."""
     intensity = np.zeros(mesh.f.shape[0], dtype=np.double, order='C')
     lo, hi, _ = _bounds(opt)
-    renderer.renderStreamedTriangleIntensity(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, intensity)
+    renderer.renderStreamedTriangleIntensity(opt.lighting, opt.lighting_normal, mesh.v, mesh.f, opt.sample_num, lo, hi, intensity, ctx=ctx)
     threshold = 0
     keep_face = np.logical_or((intensity > threshold), np.sum(mesh.f_affinity < 0, axis=1) == 0)
     print('remove #face:%d' % (mesh.f.shape[0] - np.sum(keep_face)))
@@ -138,10 +134,10 @@ def forwardRendering(mesh, opt):
     return transient, pathlengths
 
 
-def renderStreamedNormalSmoothing(mesh):
+def renderStreamedNormalSmoothing(mesh, ctx=None):
     """:299-302"""
     gradient = np.zeros(mesh.v.shape, dtype=np.double, order='C')
-    val = renderer.renderStreamedNormalSmoothing(mesh.v, mesh.f, mesh.f_affinity, gradient)
+    val = renderer.renderStreamedNormalSmoothing(mesh.v, mesh.f, mesh.f_affinity, gradient, ctx=ctx)
     return val, gradient
 
 

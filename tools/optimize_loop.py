@@ -10,7 +10,7 @@ What is and is not reproduced:
   * ground-truth transient: rendered by this library from the GT armadillo (the reference's main_create_gt.py does the same
     with its own renderer).
 
-    python tools/optimize_loop.py [--iters 50] [--wall 64] [--device]
+    python tools/optimize_loop.py [--iters 50] [--wall 64] [--device]        (the CPU baseline beside it: python bench.py --config arm)
 
 --device (device-resident iteration): vertices, target, weight, transient, gradient, loss and the Adam state stay
 in HBM as torch CUDA tensors (the renderer uses them in place), so an iteration moves no [L,B] array over PCIe and runs no
@@ -20,87 +20,38 @@ import argparse, json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import numpy as np
 import nlos_surface_optimization_b200 as nb
-from nlos_surface_optimization_b200 import rendering, scenes
+from nlos_surface_optimization_b200 import rendering, scenes, loop
 
 
-class OPT(object):           # exp_bunny/test.py:16-46
-    max_distance_bin = 1200
-    distance_resolution = 1.2 * 10 ** -3
-    normal = 'fn'
-    smooth_weight = 0.0001
-    gamma = 0
-    bin_refine_resolution = 10
-    sigma_bin = 1
-    testing_flag = 1
-    loss_flag = 0
-    alpha_flag = False
-    albedo_flag = False
-    jitter = False
-
-    def __init__(self, sample_num, resolution):
-        self.sample_num = sample_num
-        self.lighting, self.lighting_normal = scenes.wall_grid(resolution)
-
-
-class MESH(object):
-    pass
-
-
-class AdamModified(object):  # exp_bunny/adam_modified.py:60-107 (lr, betas=(0.9,0.999), eps=1e-8; denominator averaged over xyz)
-    def __init__(self, shape, lr):
-        self.m = np.zeros(shape, np.float32); self.v = np.zeros(shape, np.float32); self.t = 0; self.lr = lr
-
-    def step(self, p, g):
-        b1, b2, eps = 0.9, 0.999, 1e-8
-        self.t += 1
-        self.m = b1 * self.m + (1 - b1) * g
-        self.v = b2 * self.v + (1 - b2) * g * g
-        denom = (np.sqrt(self.v) + eps).mean(axis=1, keepdims=True)
-        step = self.lr * np.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
-        return (p - step * self.m / denom).astype(np.float32)
+def setup(args, ctx):
+    o, n = scenes.wall_grid(args.wall)
+    opt = loop.RenderOptions(20000, o, n)
+    gv, gf = scenes.armadillo(); iv, iF = scenes.armadillo_init()
+    gt_mesh = loop.Mesh(gv, gf)
+    gt_opt = loop.RenderOptions(int(4 * gf.shape[0]), o, n)                  # spp = 4 for the target
+    t0 = time.perf_counter()
+    gt_transient, _ = rendering.forwardRendering(gt_mesh, gt_opt)
+    t_gt = time.perf_counter() - t0
+    weight = rendering.create_weighting_function(gt_transient, opt.gamma)
+    return opt, gt_transient, weight, loop.Mesh(iv, iF), t_gt
 
 
 def run_device(args):
-    import torch
-    from nlos_surface_optimization_b200 import renderer
-    ctx = nb.default_context(0); dev = torch.device('cuda', 0)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    opt = OPT(20000, args.wall)
-    gv, gf = scenes.armadillo(); iv, iF = scenes.armadillo_init()
-    L, B = opt.lighting.shape[0], opt.max_distance_bin
-    lo, hi, res = 0.0, opt.max_distance_bin * opt.distance_resolution, opt.distance_resolution
-    with torch.cuda.stream(ext):
-        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        d_o, d_n = to(opt.lighting), to(opt.lighting_normal)
-        gt = torch.zeros((L, B), dtype=torch.float64, device=dev); pl = torch.zeros(B, dtype=torch.float64, device=dev)
-        renderer.renderStreamedTransient(d_o, d_n, to(gv), to(gf), int(4 * gf.shape[0]), lo, hi, res, gt, pl, 1, 1, ctx=ctx)
-        weight = torch.ones((L, B), dtype=torch.float64, device=dev)                     # create_weighting_function(gamma=0) == 1
-        v = to(iv); f = to(iF); aff = to(scenes.face_affinity(iF))
-        T = torch.zeros((L, B), dtype=torch.float64, device=dev); G = torch.zeros((iv.shape[0], 3), dtype=torch.float64, device=dev)
-        S = torch.zeros((iv.shape[0], 3), dtype=torch.float64, device=dev)
-        m = torch.zeros_like(v); s2 = torch.zeros_like(v); lr, b1, b2, eps = 0.0001 / 3, 0.9, 0.999, 1e-8
-        ext.synchronize()
-        losses, times = [], []
-        for it in range(args.iters):
-            t0 = time.perf_counter()
-            G.zero_()
-            renderer.renderStreamedGradient(d_o, d_n, v, f, opt.sample_num, lo, hi, res, T, pl, G, gt, weight, opt.bin_refine_resolution, opt.sigma_bin,
-                                            opt.testing_flag, opt.loss_flag, ctx=ctx)
-            renderer.renderStreamedNormalSmoothing(v, f, aff, S, ctx=ctx)                 # value read-back is one double
-            l2 = ((T - gt) ** 2 * weight).sum() / L                                       # evaluate_loss_with_normal_smoothness, on device
-            g = (G + opt.smooth_weight * S).to(torch.float32)
-            m.mul_(b1).add_(g, alpha=1 - b1); s2.mul_(b2).addcmul_(g, g, value=1 - b2)
-            denom = (s2.sqrt() + eps).mean(dim=1, keepdim=True)
-            step = lr * (1 - b2 ** (it + 1)) ** 0.5 / (1 - b1 ** (it + 1))
-            v.addcdiv_(m, denom, value=-step)
-            losses.append(float(l2.item()))                                               # the only D2H of the iteration (8 bytes)
-            times.append(time.perf_counter() - t0)
-    print(json.dumps({'config': 'C-arm --device (N1: device-resident iteration)', 'mesh': 'armadillo init V=%d F=%d (fixed topology)' % (iv.shape[0], iF.shape[0]),
-                      'wall': args.wall, 'iterations': args.iters, 'ms_per_iteration_mean': 1e3 * float(np.mean(times[1:])),
-                      'ms_per_iteration_median': 1e3 * float(np.median(times)), 'l2_first': losses[0], 'l2_last': losses[-1],
-                      'l2_decreased': bool(losses[-1] < losses[0]), 'kernels_launched': ctx.launch_count()}))
-    del d_o, d_n, gt, pl, weight, v, f, aff, T, G, S, m, s2
-    import gc; gc.collect(); torch.cuda.synchronize(); torch.cuda.empty_cache()
+    ctx = nb.default_context(0)
+    opt, gt_transient, weight, mesh, t_gt = setup(args, ctx)
+    it = loop.DeviceIteration(mesh, gt_transient, weight, opt, 0.0001 / 3, ctx=ctx)
+    losses, times = [], []
+    for i in range(args.iters):
+        t0 = time.perf_counter()
+        losses.append(it.step()[1])                                          # the only D2H of the iteration (16 bytes)
+        times.append(time.perf_counter() - t0)
+    out = {'config': 'C-arm --device (N1: device-resident iteration, loop.DeviceIteration)', 'mesh': 'armadillo init V=%d F=%d (fixed topology)' % (mesh.v.shape[0], mesh.f.shape[0]),
+           'wall': args.wall, 'iterations': args.iters, 'ms_per_iteration_mean': 1e3 * float(np.mean(times[1:])),
+           'ms_per_iteration_median': 1e3 * float(np.median(times)), 'l2_first': losses[0], 'l2_last': losses[-1],
+           'l2_decreased': bool(losses[-1] < losses[0]), 'kernels_launched': ctx.launch_count()}
+    print(json.dumps(out))
+    del it
+    import gc, torch; gc.collect(); torch.cuda.synchronize(); torch.cuda.empty_cache()
 
 
 if __name__ == '__main__':
@@ -111,29 +62,16 @@ if __name__ == '__main__':
         run_device(args)
         sys.exit(0)
     ctx = nb.default_context(0)
-    opt = OPT(20000, args.wall)
-    gt = MESH(); gt.v, gt.f = scenes.armadillo()
-    gt_opt = OPT(int(4 * gt.f.shape[0]), args.wall)                          # spp = 4 for the target
-    t0 = time.perf_counter()
-    gt_transient, _ = rendering.forwardRendering(gt, gt_opt)
-    t_gt = time.perf_counter() - t0
-    weight = rendering.create_weighting_function(gt_transient, opt.gamma)
-    mesh = MESH(); mesh.v, mesh.f = scenes.armadillo_init()
-    mesh.f_affinity = scenes.face_affinity(mesh.f)
-    adam = AdamModified(mesh.v.shape, 0.0001 / 3)                             # exp_bunny/test.py:56
+    opt, gt_transient, weight, mesh, t_gt = setup(args, ctx)
+    it = loop.HostIteration(mesh, gt_transient, weight, opt, 0.0001 / 3, ctx=ctx)        # exp_bunny/test.py:56
     losses, times, gpu_ms = [], [], []
     ctx.set_option('timing', 1)
-    for it in range(args.iters):
+    for i in range(args.iters):
         t0 = time.perf_counter()
-        transient, grad, _ = rendering.inverseRendering(mesh, gt_transient, weight, opt)
-        gpu_ms.append(ctx.timing())
-        smoothing_val, smoothing_grad = rendering.renderStreamedNormalSmoothing(mesh)
-        loss, l2 = rendering.evaluate_loss_with_normal_smoothness(gt_transient, weight, transient, smoothing_val, mesh, opt)
-        g = (grad + opt.smooth_weight * smoothing_grad).astype(np.float32)
-        mesh.v = np.ascontiguousarray(adam.step(mesh.v, g))
-        times.append(time.perf_counter() - t0); losses.append(float(l2))
-    print(json.dumps({'config': 'C-arm', 'mesh': 'armadillo init V=%d F=%d (fixed topology: El Topo/CGAL remeshing absent)' % (mesh.v.shape[0], mesh.f.shape[0]),
-                      'wall': args.wall, 'iterations': args.iters, 'ms_per_iteration_mean': 1e3 * float(np.mean(times[1:])),
-                      'ms_per_iteration_median': 1e3 * float(np.median(times)), 'gt_render_s': t_gt, 'library_call_ms_mean': {k: float(np.mean([g[k] for g in gpu_ms[1:]])) for k in gpu_ms[0]},
-                      'l2_first': losses[0], 'l2_last': losses[-1], 'l2_decreased': bool(losses[-1] < losses[0]),
-                      'kernels_launched': ctx.launch_count()}))
+        losses.append(it.step()[1])
+        times.append(time.perf_counter() - t0)
+    out = {'config': 'C-arm (host arrays through the facade, loop.HostIteration)', 'mesh': 'armadillo init V=%d F=%d (fixed topology: El Topo/CGAL remeshing absent)' % (mesh.v.shape[0], mesh.f.shape[0]),
+           'wall': args.wall, 'iterations': args.iters, 'ms_per_iteration_mean': 1e3 * float(np.mean(times[1:])),
+           'ms_per_iteration_median': 1e3 * float(np.median(times)), 'gt_render_s': t_gt,
+           'l2_first': losses[0], 'l2_last': losses[-1], 'l2_decreased': bool(losses[-1] < losses[0]), 'kernels_launched': ctx.launch_count()}
+    print(json.dumps(out))
