@@ -23,12 +23,14 @@ namespace {
 constexpr int kThreads = 256;
 inline int blocks_for(int64_t n, int t = kThreads) { return (int)((n + t - 1) / t); }
 
+// a face index outside [0, V) is clamped (memory safety) and counted (the call then fails with NLOS_ERR_INVALID, nlos_abi.cu)
+__device__ __forceinline__ int clampv(int i, int V) { return i < 0 ? 0 : (i >= V ? V - 1 : i); }
 __device__ __forceinline__ f3 ldv(const float* __restrict__ v, int i) { return mk3(__ldg(v + 3 * (size_t)i), __ldg(v + 3 * (size_t)i + 1), __ldg(v + 3 * (size_t)i + 2)); }
 
 __global__ void k_init_bounds(SceneBounds* sb) {
   if (threadIdx.x == 0) {
     for (int a = 0; a < 3; ++a) { sb->lo[a] = sb->vlo[a] = f2ord(3.0e38f); sb->hi[a] = sb->vhi[a] = f2ord(-3.0e38f); }
-    sb->absmax = 0u; sb->pad_ = 0u;
+    sb->absmax = 0u; sb->bad_faces = 0u;
   }
 }
 
@@ -40,12 +42,14 @@ __global__ void k_absmax(const float* __restrict__ a, size_t n, SceneBounds* sb)
   if ((threadIdx.x & 31) == 0) atomicMax(&sb->absmax, (unsigned)__float_as_int(m));   // m >= 0: int order == float order
 }
 
-__global__ void k_scene_bounds(const float* __restrict__ verts, const int* __restrict__ faces, int F, SceneBounds* sb) {
+__global__ void k_scene_bounds(const float* __restrict__ verts, int V, const int* __restrict__ faces, int F, SceneBounds* sb) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   float vl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, vh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};     // bounds of the vertices the faces use
   if (f < F) {
-    const f3 a = ldv(verts, faces[3 * (size_t)f]), b = ldv(verts, faces[3 * (size_t)f + 1]), c = ldv(verts, faces[3 * (size_t)f + 2]);
+    const int i1 = faces[3 * (size_t)f], i2 = faces[3 * (size_t)f + 1], i3 = faces[3 * (size_t)f + 2];
+    if (i1 < 0 || i1 >= V || i2 < 0 || i2 >= V || i3 < 0 || i3 >= V) atomicAdd(&sb->bad_faces, 1u);
+    const f3 a = ldv(verts, clampv(i1, V)), b = ldv(verts, clampv(i2, V)), c = ldv(verts, clampv(i3, V));
     vl[0] = fminf(a.x, fminf(b.x, c.x)); vh[0] = fmaxf(a.x, fmaxf(b.x, c.x));
     vl[1] = fminf(a.y, fminf(b.y, c.y)); vh[1] = fmaxf(a.y, fmaxf(b.y, c.y));
     vl[2] = fminf(a.z, fminf(b.z, c.z)); vh[2] = fmaxf(a.z, fmaxf(b.z, c.z));
@@ -68,10 +72,10 @@ __global__ void k_scene_bounds(const float* __restrict__ verts, const int* __res
   }
 }
 
-__global__ void k_morton_keys(const float* __restrict__ verts, const int* __restrict__ faces, int F, const SceneBounds* __restrict__ sb, uint64_t* __restrict__ keys) {
+__global__ void k_morton_keys(const float* __restrict__ verts, int V, const int* __restrict__ faces, int F, const SceneBounds* __restrict__ sb, uint64_t* __restrict__ keys) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
-  const f3 a = ldv(verts, faces[3 * (size_t)f]), b = ldv(verts, faces[3 * (size_t)f + 1]), c = ldv(verts, faces[3 * (size_t)f + 2]);
+  const f3 a = ldv(verts, clampv(faces[3 * (size_t)f], V)), b = ldv(verts, clampv(faces[3 * (size_t)f + 1], V)), c = ldv(verts, clampv(faces[3 * (size_t)f + 2], V));
   const float cx = 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x)));
   const float cy = 0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y)));
   const float cz = 0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z)));
@@ -82,13 +86,13 @@ __global__ void k_morton_keys(const float* __restrict__ verts, const int* __rest
 }
 
 // Morton-ordered triangle records and padded leaf boxes.
-__global__ void k_tri_records(const float* __restrict__ verts, const int* __restrict__ faces, int F, const uint64_t* __restrict__ keys,
+__global__ void k_tri_records(const float* __restrict__ verts, int V, const int* __restrict__ faces, int F, const uint64_t* __restrict__ keys,
                               const SceneBounds* __restrict__ sb, float4* __restrict__ ttris, float4* __restrict__ stris,
                               float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= F) return;
   const int f = (int)(uint32_t)keys[p];
-  const int i1 = faces[3 * (size_t)f], i2 = faces[3 * (size_t)f + 1], i3 = faces[3 * (size_t)f + 2];
+  const int i1 = clampv(faces[3 * (size_t)f], V), i2 = clampv(faces[3 * (size_t)f + 1], V), i3 = clampv(faces[3 * (size_t)f + 2], V);
   const f3 v1 = ldv(verts, i1), v2 = ldv(verts, i2), v3 = ldv(verts, i3);
   const TriRec tr = make_tri(v1, v2, v3);
   ttris[4 * (size_t)p + 0] = make_float4(tr.v0.x, tr.v0.y, tr.v0.z, __int_as_float(f));
@@ -200,14 +204,14 @@ void build_scene(Ctx& cx, const float* d_verts, int V, const int* d_faces, int F
   k_init_bounds<<<1, 32, 0, st>>>(sb);
   k_absmax<<<std::min(blocks_for(3 * (int64_t)V), 1024), kThreads, 0, st>>>(d_verts, 3 * (size_t)V, sb);
   if (L > 0) k_absmax<<<std::min(blocks_for(3 * L), 1024), kThreads, 0, st>>>(d_origin, 3 * (size_t)L, sb);
-  k_scene_bounds<<<blocks_for(F), kThreads, 0, st>>>(d_verts, d_faces, F, sb);
-  k_morton_keys<<<blocks_for(F), kThreads, 0, st>>>(d_verts, d_faces, F, sb, keys_in);
+  k_scene_bounds<<<blocks_for(F), kThreads, 0, st>>>(d_verts, V, d_faces, F, sb);
+  k_morton_keys<<<blocks_for(F), kThreads, 0, st>>>(d_verts, V, d_faces, F, sb, keys_in);
   cx.launches += 4 + (L > 0 ? 1 : 0);
   size_t tmp_bytes = 0;
   NLOS_CUDA_OK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_in, keys, F, 0, 62, st));
   void* tmp = cx.buf("sort_tmp").ensure(tmp_bytes);
   NLOS_CUDA_OK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys_in, keys, F, 0, 62, st));
-  k_tri_records<<<blocks_for(F), kThreads, 0, st>>>(d_verts, d_faces, F, keys, sb, ttris, stris, leaf_lo, leaf_hi);
+  k_tri_records<<<blocks_for(F), kThreads, 0, st>>>(d_verts, V, d_faces, F, keys, sb, ttris, stris, leaf_lo, leaf_hi);
   cx.launches += 1;
   if (F > 1) {
     k_karras<<<blocks_for(F - 1), kThreads, 0, st>>>(keys, F, first, last, child, parent_node, parent_leaf, flags);

@@ -6,6 +6,7 @@
 // The two regularisers write per-vertex results with '=' from every adjacent face in the reference (last writer
 // wins, and the writer depends on TBB scheduling).  Here the winner is deterministic: the adjacent face with the
 // HIGHEST index, which is what a serial pass in face order produces (and what the oracle restates).
+#include <algorithm>
 #include "nlos_ctx.h"
 #include "render_kernels.h"
 

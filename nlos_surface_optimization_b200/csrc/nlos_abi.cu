@@ -70,6 +70,21 @@ bool finish_out(Ctx& cx, const OutView<T>& v, cudaStream_t on = nullptr) {
   return true;
 }
 
+// Every face index must address a vertex (the reference reads out of bounds silently, TG.cpp:146-150).  Host arrays are checked here,
+// before anything is launched.  Device arrays cannot be checked without a round trip: the scene-build kernels clamp such indices (no
+// out-of-bounds access anywhere downstream, the clamped indices are what every later kernel sees) and count them; the count is read
+// back wherever the call synchronises anyway, and the call then fails with NLOS_ERR_INVALID.
+void require_valid_host_faces(const int* faces_arg, int F, int V) {
+  if (F <= 0 || is_device_ptr(faces_arg)) return;
+  for (size_t i = 0; i < 3 * (size_t)F; ++i) NLOS_REQUIRE(faces_arg[i] >= 0 && faces_arg[i] < V, "faces: vertex index out of range");
+}
+void require_no_clamped_faces(Ctx& cx, const DeviceScene& sc) {      // call only after the stream has been synchronised
+  if (!sc.bounds) return;
+  SceneBounds h;
+  NLOS_CUDA_OK(cudaMemcpy(&h, sc.bounds, sizeof h, cudaMemcpyDeviceToHost));
+  NLOS_REQUIRE(h.bad_faces == 0, "faces: vertex index out of range (results of this call are invalid)");
+}
+
 // Gaussian taps exactly as the reference builds them (TG.cpp:537-544, :350-355) plus their prefix sums
 struct TapTables { int K = 1; double sigma2 = 1; std::vector<double> w, wprefix, dprefix; };
 TapTables make_taps(float res, int r, int s) {
@@ -122,7 +137,7 @@ int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
 }
 
 // forward kernel: sample slots (source*spp + k) per warp pass, bounded by the visibility tile in shared memory
-int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 64; return std::min(std::max(c, 1), 256); }
+int forward_chunk(const Ctx& cx) { int c = cx.chunk_forward > 0 ? cx.chunk_forward : 64; return std::min(std::max(c, 1), forward_max_chunk()); }
 
 void run_job(Ctx& cx, const Job& j_in) {
   Job j = j_in;
@@ -179,9 +194,10 @@ void run_job(Ctx& cx, const Job& j_in) {
   if (j.kind == 3) o_I = stage_out(cx, "out_intensity", j.intensity, (size_t)j.F, true);
 
   bool need_sync = false, fwd_recorded = false;
+  if (j.F > 0 && j.L > 0) require_valid_host_faces(j.faces, j.F, j.V);
+  DeviceScene sc;
   if (j.F > 0 && j.L > 0) {
     // ---- K0: scene
-    DeviceScene sc;
     build_scene(cx, d_verts, j.V, d_faces, j.F, d_origin, j.L, d_vn, d_va, sc);
     float4* origin4 = cx.buf("origin4").as<float4>((size_t)j.L);
     float4* onormal4 = cx.buf("onormal4").as<float4>((size_t)j.L);
@@ -227,7 +243,12 @@ void run_job(Ctx& cx, const Job& j_in) {
       uint32_t* vis = nullptr;
       const bool want_grad = j.kind >= 0 && j.kind <= 2;
       cx.vis_words = 0;
-      if (want_grad && cx.reuse_visibility) { cx.vis_words = (size_t)j.L * P.spp * P.words_per_row; vis = cx.buf("vis").as<uint32_t>(cx.vis_words); }
+      if (want_grad && cx.reuse_visibility) {
+        // one bit per sample; when that buffer cannot be had (very large L * spp * F) the gradient pass re-traces its rays instead
+        const size_t words = (size_t)j.L * P.spp * P.words_per_row;
+        try { vis = cx.buf("vis").as<uint32_t>(words); cx.vis_words = words; }
+        catch (const std::exception&) { cudaGetLastError(); vis = nullptr; cx.vis_words = 0; }
+      }
       P.chunk = forward_chunk(cx);                                                       // sample slots per warp pass
       const double* d_jw = nullptr; const double* d_jg = nullptr;
       if (j.jlen > 0) {
@@ -303,6 +324,7 @@ void run_job(Ctx& cx, const Job& j_in) {
   if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[5], st));
   if (need_sync || timing) NLOS_CUDA_OK(cudaStreamSynchronize(st));
   if (copy_sync) NLOS_CUDA_OK(cudaStreamSynchronize(cx.copy_stream));
+  if ((need_sync || timing) && is_device_ptr(j.faces)) require_no_clamped_faces(cx, sc);
   if (timing) {
     cudaEventElapsedTime(&cx.timing.build_ms, cx.ev[0], cx.ev[1]);
     cudaEventElapsedTime(&cx.timing.forward_ms, cx.ev[1], cx.ev[2]);

@@ -8,7 +8,7 @@
 
 namespace nlos {
 
-struct SceneBounds { unsigned lo[3], hi[3]; unsigned absmax; unsigned pad_; unsigned vlo[3], vhi[3]; };   // centroid bounds, max |coordinate|, vertex bounds (ordered-uint floats)
+struct SceneBounds { unsigned lo[3], hi[3]; unsigned absmax; unsigned bad_faces; unsigned vlo[3], vhi[3]; };   // centroid bounds, max |coordinate|, count of out-of-range face indices (clamped by the build kernels), vertex bounds (ordered-uint floats)
 
 // Mesh + acceleration structure resident in HBM for the duration of one call (rebuilt per call like the
 // reference rebuilds its Embree scene, SSG.cpp:473-511).  All per-triangle arrays are in Morton order.

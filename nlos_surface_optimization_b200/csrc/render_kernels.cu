@@ -913,6 +913,10 @@ void launch_gradient_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, co
                        const double* wprefix, const double* dprefix, double* out) {
   const dim3 grid = sample_grid(sc, P);
   const size_t smem = 2 * (size_t)(P.K + 1) * sizeof(double);
+  if (smem > 48 * 1024) {      // long tap tables (refine_scale * sigma_bin >= ~768) need the opt-in shared-memory limit, as the forward kernel does
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_gradient<GGX, VN, VA, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_gradient<GGX, VN, VA, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (vis) k_gradient<GGX, VN, VA, KIND, true><<<grid, kBlock, smem, cx.stream>>>(sc, P, diff, vis, wprefix, dprefix, out);
   else k_gradient<GGX, VN, VA, KIND, false><<<grid, kBlock, smem, cx.stream>>>(sc, P, diff, vis, wprefix, dprefix, out);
   cx.launches += 1;
@@ -939,6 +943,8 @@ void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool 
 #undef NLOS_FWD
   NLOS_CUDA_OK(cudaGetLastError());
 }
+
+int forward_max_chunk() { return kTile; }      // sample slots per warp pass of k_forward == words of its visibility tile
 
 void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity) {
   if (sc.F <= 0 || P.L <= 0) return;

@@ -6,6 +6,7 @@ namespace nlos {
 
 void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* transient, uint32_t* vis, const double* wprefix);
 void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity);
+int forward_max_chunk();   // upper bound of RenderParams::chunk for the BVH forward kernel (its shared-memory visibility tile)
 void launch_residual(Ctx& cx, const double* data, const double* weight, const double* T, double* diff, size_t n, int loss_flag);
 void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, int kind, const double* diff, const uint32_t* vis,
                      const double* wprefix, const double* dprefix, double* out);

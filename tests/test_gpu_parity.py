@@ -300,6 +300,65 @@ def test_c_bunny_against_committed_oracle_goldens(fixture, gpu_ctx):
     gpu_ctx.set_source_window(0, 0)
 
 
+@pytest.mark.parametrize('fixture', ['c_ggx16', 'c_ggx'])
+def test_c_ggx_against_committed_oracle_goldens(fixture, gpu_ctx):
+    """BASELINE.json configs[2] (exp_ggx/test10.py:37,60): GGX render + gradient of the bunny, alpha = 0.1 against data rendered at
+    alpha = 0.2, on a 16x16 and on the full 64x64 wall, against oracle output committed under tests/golden (tools/make_golden.py):
+    transient <= 1e-5; vertex gradient <= 1e-4 with testing_flag 1 (face normals) and 0 (shading normals); alpha scalar <= 1e-4."""
+    import os
+    from nlos_surface_optimization_b200 import ggx, scenes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fixture + '.npz'))
+    wall, ns, alpha, alpha_data = int(g['wall']), int(g['num_sample']), float(g['alpha']), float(g['alpha_data'])
+    v, f = scenes.bunny(); o, n = scenes.wall_grid(wall); vn = scenes.vertex_normals(v, f)
+    L, B = o.shape[0], 1200
+    data = np.zeros((L, B)); pl = np.zeros(B)
+    ggx.renderStreamedTransient(o, n, v, f, alpha_data, ns, LB, UB, RES, data, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(data.sum(1), g['data_row_sum']) <= TOL_TRANSIENT and rel_l2(data.sum(0), g['data_col_sum']) <= TOL_TRANSIENT
+    weight = np.ones_like(data)
+    T = np.zeros((L, B)); G = np.zeros((v.shape[0], 3))
+    ggx.renderStreamedGradient(o, n, v, f, alpha, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(T[g['rows']], g['transient_rows']) <= TOL_TRANSIENT
+    assert rel_l2(T.sum(1), g['transient_row_sum']) <= TOL_TRANSIENT and rel_l2(T.sum(0), g['transient_col_sum']) <= TOL_TRANSIENT
+    assert rel_l2(G, g['gradient_tf1']) <= TOL_GRADIENT
+    T0 = np.zeros((L, B)); G0 = np.zeros((v.shape[0], 3))
+    ggx.renderStreamedShadingGradient(o, n, v, f, vn, alpha, ns, LB, UB, RES, T0, pl, G0, data, weight, 10, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T0.sum(1), g['shading_transient_row_sum']) <= TOL_TRANSIENT and rel_l2(T0.sum(0), g['shading_transient_col_sum']) <= TOL_TRANSIENT
+    assert rel_l2(G0, g['gradient_tf0_shading']) <= TOL_GRADIENT
+    Ta = np.zeros((L, B))
+    ga = ggx.renderStreamedGradientAlpha(o, n, v, f, alpha, ns, LB, UB, RES, Ta, pl, data, weight, 10, 1, ctx=gpu_ctx)
+    assert abs(ga - float(g['alpha_grad'])) <= TOL_GRADIENT * abs(float(g['alpha_grad']))
+
+
+def test_c_scale_mesh_against_committed_oracle_golden(gpu_ctx):
+    """BASELINE.json configs[4] at its full mesh size (height field F = 500 000, B = 2048) on a 16x16 wall: per-sample visibility
+    digests bit-exact, transient <= 1e-5, gradient <= 1e-4 (norm, column sums, 1024-vertex block sums and every 64th row)."""
+    import os
+    import nlos_surface_optimization_b200 as nb
+    from nlos_surface_optimization_b200 import renderer, scenes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'c_scale16.npz'))
+    wall, ns, B = int(g['wall']), int(g['num_sample']), int(g['numbins'])
+    v, f = scenes.heightfield(501); o, n = scenes.wall_grid(wall)
+    assert f.shape[0] == 500000
+    L, ub = o.shape[0], B * RES
+    v2 = v.copy(); v2[:, 2] += 0.01
+    data = np.zeros((L, B)); pl = np.zeros(B)
+    renderer.renderStreamedTransient(o, n, v2, f, ns, LB, ub, RES, data, pl, 1, 1, ctx=gpu_ctx)
+    assert rel_l2(data.sum(1), g['data_row_sum']) <= TOL_TRANSIENT and rel_l2(data.sum(0), g['data_col_sum']) <= TOL_TRANSIENT
+    T = np.zeros((L, B)); G = np.zeros((v.shape[0], 3))
+    renderer.renderStreamedGradient(o, n, v, f, ns, LB, ub, RES, T, pl, G, data, np.ones_like(data), 10, 1, 1, 0, ctx=gpu_ctx)
+    assert rel_l2(T.sum(1), g['transient_row_sum']) <= TOL_TRANSIENT and rel_l2(T.sum(0), g['transient_col_sum']) <= TOL_TRANSIENT
+    assert abs((T * T).sum() - float(g['transient_sq_sum'])) <= 2 * TOL_TRANSIENT * float(g['transient_sq_sum'])
+    assert rel_l2(G[::64], g['gradient_rows']) <= TOL_GRADIENT
+    assert abs(np.linalg.norm(G) - float(g['gradient_l2'])) <= TOL_GRADIENT * float(g['gradient_l2'])
+    assert rel_l2(np.add.reduceat(G, np.arange(0, G.shape[0], 1024), axis=0), g['gradient_block_sum']) <= TOL_GRADIENT
+    slab = 32
+    for a in range(0, L, slab):
+        vis, _ = nb.debug_visibility(np.ascontiguousarray(o[a:a + slab]), v, f, ns, ctx=_windowed(gpu_ctx, a, L))
+        pop, crc = _vis_digest(vis)
+        assert np.array_equal(pop, g['vis_pop'][a:a + slab]) and np.array_equal(crc, g['vis_crc'][a:a + slab])
+    gpu_ctx.set_source_window(0, 0)
+
+
 def _windowed(ctx, offset, total):
     ctx.set_source_window(offset, total)
     return ctx

@@ -378,3 +378,23 @@ def test_jitter_kernel_restatement(oracle):
     _, Gj, _ = oracle.jitter_gradient(o, n, v, f, ns, LB, UB, RES, wg, jg, 20, Tj + D, np.ones_like(D))
     _, Gg, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, H + D, np.ones_like(D), 1, s_bin)       # sigma>=5 & r=1: forward raw
     assert rel_l2(Gj, Gg) < 1e-5
+
+
+def test_canonical_traversal_counter(oracle):
+    """the accounting traversal (Karras LBVH, one triangle per leaf, near child first, nearest hit) answers visibility exactly as
+    the oracle's own query does, and its counts follow the closed form on a mesh where that is known."""
+    from nlos_surface_optimization_b200 import scenes
+    o, n = scenes.wall_grid(4)
+    v, f = scenes.fan8()
+    c = oracle.canonical_counts(o, v, f, 8 * 64)
+    # 8 coplanar triangles, every ray hits exactly one: root-to-leaf descent of a 3-level tree tests 3 x 2 boxes and, with the boxes of
+    # neighbouring triangles touching, at most a few extra; every sample is visible
+    assert c['rays'] == o.shape[0] * 8 * 64 and c['visible_frac'] == 1.0
+    assert 6.0 <= c['box_per_ray'] <= 12.0 and 1.0 <= c['tri_per_ray'] <= 3.0
+    v, f = scenes.icosphere(3, 0.1, (0.02, -0.03, 0.45), noise=0.03, seed=3)
+    ns = 2 * f.shape[0]
+    vis = oracle.transient(o, n, v, f, ns, LB, UB, RES, want_visibility=True)[2]
+    c = oracle.canonical_counts(o, v, f, ns)
+    assert c['rays'] == vis.size and abs(c['visible_frac'] * c['rays'] - vis.sum()) < 0.5
+    import math
+    assert c['box_per_ray'] >= 2 * math.floor(math.log2(f.shape[0])) * 0.5 and c['tri_per_ray'] >= 1.0

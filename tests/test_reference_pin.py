@@ -74,6 +74,12 @@ SAME = rc.same_sample_cases()
 # and with only 20 samples per triangle each such sample weighs ~5e-5 of the output norm.  Hence two bars: raw-histogram outputs 1e-4,
 # outputs built on fine bins 5e-4.  (A wrong formula, constant or index shows up at 1e-2 ... 1.)
 TOL_SAME = {'T': 1e-4, 'I': 2e-5, 'G': 5e-4, 'g': 5e-4, 'VG': 5e-4}
+# That explanation is ASSERTED, not just offered (ref_cases.assert_residual_is_a_few_flipped_samples): the residual of every array
+# output is localized — in a transient a few short runs of neighbouring bins (<= 8 per case; 0 in 27 of the 38 transient outputs), in
+# a gradient the three vertex rows of at most two triangles (bunny: 155 of 34 817 rows) — and OUTSIDE those events the two sides agree
+# to <= 1e-6 (transients, intensities; measured 2e-8 ... 6e-7) and <= 2e-5 (gradients; measured 8e-8 ... 1.4e-5), i.e. the north
+# star's 1e-5 / 1e-4 with margin.  The reference side runs plain mul/add code (g++ without FMA contraction), the oracle and the CUDA
+# path the pinned fmaf order, so the last bits of r differ by construction and the flips cannot be removed by compiler flags.
 
 
 @pytest.mark.parametrize('name', sorted(SAME))
@@ -88,6 +94,7 @@ def test_oracle_matches_reference_on_the_reference_sample_stream(name, oracle):
         print('same/%s/%s rel %.2e' % (name, key, err))
         tol = 5e-4 if (key == 'T' and c.get('rs', 1) > 1 and c['kind'] == 'transient') else TOL_SAME[key]
         assert np.linalg.norm(want) > 0 and err <= tol, (name, key, err)
+        rc.assert_residual_is_a_few_flipped_samples(c, name, key, val, want)
 
 
 def test_regularisers_match_reference(oracle):
@@ -303,3 +310,4 @@ def test_cuda_path_matches_reference_on_the_reference_sample_stream(name, oracle
         print('same(gpu)/%s/%s rel %.2e' % (name, key, err))
         tol = 5e-4 if (key == 'T' and c.get('rs', 1) > 1 and c['kind'] == 'transient') else TOL_SAME[key]
         assert np.linalg.norm(want) > 0 and err <= tol, (name, key, err)
+        rc.assert_residual_is_a_few_flipped_samples(c, name, key, val, want)
