@@ -434,7 +434,8 @@ def roofline_record(env, p, phase, counters, ms_per_step, mb, sm_count, peaks, c
     samples = L * F * spp
     achieved = samples * fl_fwd / (fwd_ms * 1e-3) / 1e12
     peak, peak_how = mb.fp32(sm_count)
-    grid_used = counters.get('samples_generated', 0) > 0
+    grid_used = counters.get('forward_algo', 0) == 2
+    counted = counters.get('samples_generated', 0) > 0
     rec = {'bound': 'fp32', 'kernel': 'k_forward_grid' if grid_used else 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
            'peak_source': peak_how, 'kernel_ms': fwd_ms,
            'canonical': {'box_tests_per_path_sample': can['box_per_ray'], 'tri_tests_per_path_sample': can['tri_per_ray'], 'visible_fraction': rho,
@@ -448,14 +449,14 @@ def roofline_record(env, p, phase, counters, ms_per_step, mb, sm_count, peaks, c
             rec['traffic'] = tr[rec['kernel']]['dram_bytes']; rec['traffic_source'] = tr[rec['kernel']].get('source')
     except Exception:
         pass
-    if grid_used:
+    if counted:
         c = counters
         fl_exec = (L * V * 25.0 + L * F * 24.0 + L * F * 30.0 + c['samples_generated'] * (FL_GEN + FL_TRI) + c['rays_traced'] * (FL_SHADE_FWD + 12 + (FL_GGX_FWD if ggx_on else 0)) + c['cell_check_passes'] * FL_TRI)
         rec['executed'] = {'counters': c, 'flops': fl_exec, 'TFLOPs': fl_exec / (fwd_ms * 1e-3) / 1e12, 'frac_of_peak': fl_exec / (fwd_ms * 1e-3) / 1e12 / peak,
                            'int_entry_checks': c['entry_words_scanned'], 'int_entry_checks_per_s': c['entry_words_scanned'] / (fwd_ms * 1e-3),
                            'pricing': 'per (source, vertex) projection 25; per (source, triangle) rectangle 24 + plane-side cull 30; per generated sample 32 + 50 (self intersection); per traced ray 48 (+30 GGX) shade + 12 cell lookup; per cell-level check pass one 50-flop triangle test; the entry scan is integer work (3 ops per word), listed separately'}
     # gradient kernel: effective rate and its L2 atomics
-    vis = counters.get('visible_samples', 0) if grid_used else rho * samples
+    vis = counters.get('visible_samples', 0) if counted else rho * samples
     fl_bwd_exec = vis * (FL_GEN + FL_TRI + FL_SHADE_BWD + (FL_GGX_BWD if ggx_on else 0))
     fl_bwd_can = samples * (FL_GEN + FL_BOX * can['box_per_ray'] + FL_TRI * can['tri_per_ray'] + rho * (FL_SHADE_BWD + (FL_GGX_BWD if ggx_on else 0)))
     red_T = mb.red_f64(L * B); red_G = mb.red_f64(3 * V)
@@ -517,7 +518,7 @@ def run_render_config(env, args, mb):
                        sc['label'], p['L'], (' of a %dx%d wall (weak scaling)' % (sc['wall'] * env.world, sc['wall'])) if (env.world > 1 and args.config != 'scale') else '',
                        ' + NCCL all-reduce' if env.world > 1 else ''),
                    'l2': 'flushed between timed iterations (256 MiB write)', 'ms_per_iteration': ms_per_step, 'wall_ms_per_step_incl_flush': 1e3 * t_wall / steps,
-                   'phase_ms': phase, 'visibility_reuse': True, 'forward_kernel': 'k_forward_grid (perspective grid, G=%d)' % counters['grid_res'] if counters.get('samples_generated', 0) > 0 else 'k_forward (BVH traversal)',
+                   'phase_ms': phase, 'visibility_reuse': True, 'forward_kernel': 'k_forward_grid (perspective grid, G=%d)' % counters['grid_res'] if counters.get('forward_algo', 0) == 2 else 'k_forward (BVH traversal)',
                    'value_counts': '2*L*F*spp path samples per step (SURVEY 8d); the gradient pass reuses the forward visibility bits and traces no rays'},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }

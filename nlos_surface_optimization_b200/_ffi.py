@@ -178,7 +178,7 @@ class Context(object):
         """MEASUREMENT: work counters of the last perspective-grid forward launch run with option count_work = 1."""
         buf = (C.c_uint64 * 8)()
         self.check(self.lib.nlos_ctx_get_work_counters(self.handle, buf), 'nlos_ctx_get_work_counters')
-        keys = ('samples_generated', 'rays_traced', 'entry_words_scanned', 'cell_check_passes', 'visible_samples', 'sources_without_grid', 'grid_res')
+        keys = ('samples_generated', 'rays_traced', 'entry_words_scanned', 'cell_check_passes', 'visible_samples', 'sources_without_grid', 'grid_res', 'forward_algo')
         return dict(zip(keys, [int(x) for x in buf]))
 
     def visibility_words(self):

@@ -470,7 +470,7 @@ int nlos_ctx_get_work_counters(nlos_ctx* ctx, uint64_t* out8) {
     NLOS_CUDA_OK(cudaStreamSynchronize(cx.stream));
     for (int i = 0; i < 8; ++i) out8[i] = 0;
     if (cx.buf("work_counters").p) NLOS_CUDA_OK(cudaMemcpy(out8, cx.buf("work_counters").p, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    out8[6] = (uint64_t)cx.work_G;
+    out8[6] = (uint64_t)cx.last_grid_res; out8[7] = (uint64_t)cx.last_forward_algo;
     return NLOS_OK;
   } catch (const std::exception& e) { cx.last_error = e.what(); cudaGetLastError(); return NLOS_ERR_CUDA; }
 }

@@ -52,6 +52,8 @@ struct Ctx {
   int grid_res = 0;              // cells per axis of the perspective grid (0 = auto from the triangle count)
   int count_work = 0;            // measurement: the next perspective-grid forward launch fills buf("work_counters") (nlos_ctx_get_work_counters)
   int work_G = 0;                // grid resolution of that launch
+  int last_forward_algo = 0;     // forward kernel of the last call: 1 BVH traversal, 2 perspective grid
+  int last_grid_res = 0;
   int grid_cap = 0;              // test hook: upper bound of the per-source entry budget of the perspective grid (0 = none); forces the coarsening path
   size_t vis_words = 0;          // words of the last call's visibility buffer (nlos_debug_copy_visibility_words)
   int num_sms = 0;               // multiprocessors of the device (filled at context creation)

@@ -359,7 +359,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned* a, int n, uns
   return total;
 }
 
-template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE>
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE, bool COUNT>
 __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_grid(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
                                                     const GridScratch scr, unsigned cap, int G0) {
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
     }
     // ---------------- pass 3: samples
     const bool grid = gs.use_grid != 0;
-    if (scr.counters && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
+    if (COUNT && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
     const PGridFrame fr = gs.fr;
     const int G = fr.G;
     for (int base = warp * 32; base < F; base += kGridBlock) {
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
                 }
               }
             }
-            nhit += __popc(mask);
+            if (COUNT) nhit += __popc(mask);
             // pooled exact tests: every lane hands up to kGridPush candidates to the warp's pool, then all 32 lanes work the pool
             while (__any_sync(0xffffffffu, mask != 0u)) {
               const int nb = __popc(mask);
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           __syncwarp();
           occ = occ || ((gw.occ >> lane) & 1u);
           __syncwarp();                                                             // gw is rewritten by the next sample
-          if (scr.counters) {                                                       // measurement runs only (bench.py roofline.executed)
+          if (COUNT) {                                                              // measurement instantiation only (bench.py roofline.executed)
             const unsigned c1 = __reduce_add_sync(0xffffffffu, need ? 1u : 0u), c2 = __reduce_add_sync(0xffffffffu, (unsigned)(4 * ngrp)), c3 = __reduce_add_sync(0xffffffffu, nhit);
             const unsigned c0 = __reduce_add_sync(0xffffffffu, culled ? 0u : 1u), c4 = __reduce_add_sync(0xffffffffu, (need && !occ) ? 1u : 0u);
             if (lane == 0) { atomicAdd(scr.counters, (unsigned long long)c0); atomicAdd(scr.counters + 1, (unsigned long long)c1); atomicAdd(scr.counters + 2, (unsigned long long)c2);
@@ -877,25 +877,34 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
   scr.entE = cx.buf("grid_entE").as<unsigned>((size_t)blocks * cap);
   scr.entI = cx.buf("grid_entI").as<unsigned>((size_t)blocks * cap);
+  cx.last_forward_algo = 2; cx.last_grid_res = G;
   scr.counters = nullptr;
+  // work counters (option "count_work"): a separate instantiation, only for the Lambertian face-normal transient kernels (the headline)
+  constexpr bool kCanCount = !GGX && !VN && !VA && MODE == 0;
+  const bool count = kCanCount && cx.count_work != 0;
   if (cx.count_work) {
     scr.counters = cx.buf("work_counters").as<unsigned long long>(8);
     NLOS_CUDA_OK(cudaMemsetAsync(scr.counters, 0, 8 * sizeof(unsigned long long), cx.stream));
-    cx.work_G = G;
+    cx.work_G = count ? G : 0;
   }
-  if (vis) {
-    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_forward_grid<GGX, VN, VA, SMOOTH, true, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);
+#define NLOS_GRID_LAUNCH(WV, CNT)                                                                                                              \
+  do {                                                                                                                                         \
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);           \
+  } while (0)
+  if (count) {
+    if constexpr (kCanCount) { if (vis) NLOS_GRID_LAUNCH(true, true); else NLOS_GRID_LAUNCH(false, true); }
   } else {
-    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_forward_grid<GGX, VN, VA, SMOOTH, false, MODE><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);
+    if (vis) NLOS_GRID_LAUNCH(true, false); else NLOS_GRID_LAUNCH(false, false);
   }
+#undef NLOS_GRID_LAUNCH
   cx.launches += 1;
 }
 
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
   if (use_grid_forward(cx, sc, P)) { launch_forward_grid_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
+  cx.last_forward_algo = 1; cx.last_grid_res = 0;
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
   const dim3 grid((unsigned)((sc.F + 31) / 32), (unsigned)std::min<int64_t>((nchunks + kFwdBlock / 32 - 1) / (kFwdBlock / 32), 65535), 1);
   const size_t smem = (kFwdBlock / 32) * sizeof(WarpShared) + (SMOOTH ? (size_t)(P.K + 1) * sizeof(double) : 0);
