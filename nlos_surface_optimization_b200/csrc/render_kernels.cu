@@ -317,7 +317,7 @@ constexpr int kGridPush = 8;               // candidates a lane hands to the war
 constexpr int kGridPool = 32 * kGridPush;  // (ray, candidate) work items per round
 struct GridWarp {                          // per-warp scratch of pass 3
   float dx[32], dy[32], dz[32], ts[32]; int prim[32];   // the warp's rays, readable by every lane
-  unsigned pool[kGridPool];                // work items: ray lane << 27 | entry position
+  unsigned pool[kGridPool];                // work items: ray lane << 27 | candidate triangle (Morton index)
   unsigned occ;                            // bit l: the ray of lane l is occluded
   unsigned pad_[3];
 };
@@ -435,25 +435,41 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
       const int G = fr.G, ncell = G * G * kGridK;
       for (int i = tid; i < ncell; i += kGridBlock) cells[i] = 0u;
       __syncthreads();
-      for (int p = tid; p < F; p += kGridBlock) {
-        const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
-        const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
-        int a0, a1, b0, b1;
-        pg_tri_rect(fr, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, pad_u, pad_v, a0, a1, b0, b1);
-        // depth slice of the triangle's nearest vertex: it can only occlude rays whose own hit is at least that deep
-        const int kz = pg_quant(fminf(p1.z, fminf(p2.z, p3.z)) - pad_z, z0, sz, (float)(kGridK - 1));
-        trect[p] = make_uint2((unsigned)a0 | ((unsigned)a1 << 16) | ((unsigned)(kz & 1) << 15) | ((unsigned)(kz >> 1) << 31), (unsigned)b0 | ((unsigned)b1 << 16));
-        const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
-        const int cy0 = b0 >> kPgSub;
-        if (cx0 == cx1 && cy0 == cy1) atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);       // the common case: one cell
-        else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+      // two-stage software pipeline: the vertex indices of triangle p + 2*stride and the projected vertices of p + stride are in
+      // flight while triangle p is binned (each is a dependent L2 round trip otherwise: 11 % of the kernel's stall samples)
+      {
+        int p = tid;
+        float4 s3n = make_float4(0.f, 0.f, 0.f, 0.f), q1 = s3n, q2 = s3n, q3 = s3n;
+        if (p < F) {
+          const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+          q1 = proj[__float_as_int(s3.y)]; q2 = proj[__float_as_int(s3.z)]; q3 = proj[__float_as_int(s3.w)];
+          if (p + kGridBlock < F) s3n = __ldg(sc.stris + 4 * (size_t)(p + kGridBlock) + 3);
+        }
+        for (; p < F; p += kGridBlock) {
+          const float4 p1 = q1, p2 = q2, p3 = q3;
+          if (p + kGridBlock < F) {
+            q1 = proj[__float_as_int(s3n.y)]; q2 = proj[__float_as_int(s3n.z)]; q3 = proj[__float_as_int(s3n.w)];
+            if (p + 2 * kGridBlock < F) s3n = __ldg(sc.stris + 4 * (size_t)(p + 2 * kGridBlock) + 3);
+          }
+          int a0, a1, b0, b1;
+          pg_tri_rect(fr, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, pad_u, pad_v, a0, a1, b0, b1);
+          // depth slice of the triangle's nearest vertex: it can only occlude rays whose own hit is at least that deep
+          const int kz = pg_quant(fminf(p1.z, fminf(p2.z, p3.z)) - pad_z, z0, sz, (float)(kGridK - 1));
+          trect[p] = make_uint2((unsigned)a0 | ((unsigned)a1 << 16) | ((unsigned)(kz & 1) << 15) | ((unsigned)(kz >> 1) << 31), (unsigned)b0 | ((unsigned)b1 << 16));
+          const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
+          const int cy0 = b0 >> kPgSub;
+          if (cx0 == cx1 && cy0 == cy1) atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);       // the common case: one cell
+          else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+        }
       }
       __syncthreads();
       const unsigned total = block_exclusive_scan(cells, ncell, gs.wsum);
       __syncthreads();
       if (total <= cap) {
+        uint2 rn = tid < F ? trect[tid] : make_uint2(0u, 0u);                                  // next triangle's rectangle in flight while this one is scattered
         for (int p = tid; p < F; p += kGridBlock) {
-          const uint2 r = trect[p];
+          const uint2 r = rn;
+          if (p + kGridBlock < F) rn = trect[p + kGridBlock];
           const int a0 = (int)(r.x & 0x7fffu), a1 = (int)((r.x >> 16) & 0x7fffu), b0 = (int)(r.y & 0xffffu), b1 = (int)(r.y >> 16);
           const int kz = (int)((r.x >> 15) & 1u) | (int)((r.x >> 31) << 1);
           const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
@@ -567,13 +583,15 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
               for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += y; }
               const int total = __shfl_sync(0xffffffffu, incl, 31);
               int off = incl - n;
-              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | (unsigned)(start + 4 * g0 + bpos); }
+              // the pushing lane fetches the candidate's triangle index (up to kGridPush independent loads in flight) so that the exact-test
+              // loop below starts with the triangle fetch instead of two dependent round trips
+              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | entI[start + 4 * g0 + bpos]; }
               __syncwarp();
               for (int i = lane; i < total; i += 32) {
                 const unsigned item = gw.pool[i];
                 const int rl = (int)(item >> 27);
                 if (!((gw.occ >> rl) & 1u)) {
-                  const int tj = (int)entI[item & 0x7ffffffu];
+                  const int tj = (int)(item & 0x7ffffffu);
                   if (tj != base + rl && tri_occludes_od(sc.ttris, tj, o, mk3(gw.dx[rl], gw.dy[rl], gw.dz[rl]), gw.ts[rl], gw.prim[rl])) atomicOr(&gw.occ, 1u << rl);
                 }
               }
@@ -854,7 +872,7 @@ inline size_t grid_smem_bytes(int G, bool smooth, int K) {
 }
 // perspective-grid forward kernel: applies outside the first-generation mode (its unclamped form factor traces rays behind the wall point)
 inline bool use_grid_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
-  if (cx.forward_algo == 1 || P.sr || sc.F < 1 || sc.V < 1 || sc.bounds == nullptr || sc.verts == nullptr) return false;
+  if (cx.forward_algo == 1 || P.sr || sc.F < 1 || sc.F >= (1 << 27) || sc.V < 1 || sc.bounds == nullptr || sc.verts == nullptr) return false;   // work items pack the triangle index into 27 bits
   if (cx.forward_algo == 2) return true;
   // auto: one block per wall point needs enough wall points to fill the machine; below that the BVH kernel (finer work items) is used
   return P.L >= (cx.num_sms > 0 ? cx.num_sms : 148);
