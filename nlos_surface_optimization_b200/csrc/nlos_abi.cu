@@ -448,9 +448,12 @@ int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value) {
   else if (k == "chunk_forward") ctx->cx.chunk_forward = (int)value;
   else if (k == "chunk_gradient") ctx->cx.chunk_gradient = (int)value;
   else if (k == "timing") ctx->cx.timing_enabled = value != 0;
-  else if (k == "forward_algo") { if (value < 0 || value > 2) { ctx->cx.last_error = "forward_algo must be 0 (auto), 1 (bvh) or 2 (grid)"; return NLOS_ERR_INVALID; } ctx->cx.forward_algo = (int)value; }
+  else if (k == "forward_algo") { if (value < 0 || value > 3) { ctx->cx.last_error = "forward_algo must be 0 (auto), 1 (bvh), 2 (per-point grid) or 3 (shared grid)"; return NLOS_ERR_INVALID; } ctx->cx.forward_algo = (int)value; }
   else if (k == "count_work") ctx->cx.count_work = value != 0;
   else if (k == "grid_cap") { if (value < 0 || value > 0x7fffffff) { ctx->cx.last_error = "grid_cap out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_cap = (int)value; }
+  else if (k == "group_side") { if (value < 0 || value > 64) { ctx->cx.last_error = "group_side out of range"; return NLOS_ERR_INVALID; } ctx->cx.group_side = (int)value; }
+  else if (k == "grid_slices") { if (value < 0 || value > 64) { ctx->cx.last_error = "grid_slices out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_slices = (int)value; }
+  else if (k == "grid_budget_mb") { if (value < 0 || value > (1 << 20)) { ctx->cx.last_error = "grid_budget_mb out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_budget_mb = (int)value; }
   else if (k == "grid_res") { if (value < 0 || value > 4096) { ctx->cx.last_error = "grid_res out of range"; return NLOS_ERR_INVALID; } ctx->cx.grid_res = (int)value; }
   else { ctx->cx.last_error = "unknown option " + k; return NLOS_ERR_INVALID; }
   return NLOS_OK;

@@ -406,6 +406,197 @@ NLOS_HD void pg_coarsen(PGridFrame& g) {
 }
 NLOS_HD float pg_zmin(const float* blo, const float* bhi) { return 1.0e-3f * ((bhi[0] - blo[0]) + (bhi[1] - blo[1]) + (bhi[2] - blo[2])) + 1.0e-30f; }
 
+// ------------------------------------------------------------------ shared perspective grid of a GROUP of wall points (DESIGN.md "K1s")
+// The picture of the section above belongs to ONE projection centre.  Seen from a centre c, a ray that leaves another point
+// o' = c + delta is no longer a point of the picture, but it is a straight line of the projective space (u, v, w), w = 1/Z:
+//     u(w) = u_inf + s_u * w,   u_inf = d.a / d.n,   s_u = delta.a - (delta.n) u_inf      (v alike)
+// (for wall points of one plane delta.n = 0 and the slope is just the offset of the wall point from the centre).  So the triangles
+// are binned ONCE per group of neighbouring wall points into a 3-D grid (G x G picture cells x K slices of w); a ray visits the
+// slices from the nearest one to the slice of its own hit and, in each, tests the list of the cell that the slice-centre point of its
+// line falls into.  The line moves by at most S * dw / 2 inside a slice (S = slope bound of the group, dw = slice thickness): the
+// rectangles are expanded by that much, and rays whose slope exceeds S take the per-ray BVH query instead.
+// Every entry carries, besides the guarded rectangle bytes of the section above, three EDGE words and a fine depth index j (one of 32
+// sub-slices of its slice: the middle of the triangle's own w range).  An edge word holds one picture edge of the triangle in the
+// sub-cell units of the entry's cell (shifted by kGgBias) as signed bytes [a | b | c_hi | c_lo]: a x + b y + 255 c_hi + c_lo >= 0
+// inside, rounded OUTWARDS by the quantisation slack, the padding and the movement of a ray across the triangle's own w range.  A
+// candidate that passed the rectangle bytes is tested at the point of the ray's line at sub-slice j: one dp4a per edge against the
+// ray word [x | y | 255 | 1].  Only candidates that pass all three edges get the exact Moeller-Trumbore test — little more than the
+// ray's own triangle.  As before, the grid only SELECTS candidates: the answer is the exact float test's.
+struct GGFrame {
+  f3 o, a, b, n;            // projection centre (centre of the group), frame (n = unit wall normal of the group's first member)
+  float u0, v0, su, sv;     // uq = clamp(floor((u - u0) * su), 0, Q-1)
+  int G;                    // cells per axis (0: no grid for this group -> per-ray BVH query)
+  float qmax;               // Q - 1 as float
+  int K; float kmax;        // slices of w
+  float w1, sw, dw;         // slice of w: clamp(floor((w1 - w) * sw), 0, K-1), slice 0 = nearest; dw = 1 / sw
+  float Su, Sv;             // slope bounds |du/dw|, |dv/dw| of the rays that may use the grid
+  float pad_u, pad_v;       // round-off padding of picture coordinates
+  float eu, ev;             // expansion of a triangle's picture rectangle (padding + movement of a ray inside a slice)
+  float pad_w;              // round-off padding of w
+};
+constexpr int kGgFine = 32;                    // sub-slices per slice (5 bits beside the 27-bit triangle index)
+constexpr int kGgBias = 16;                    // shift of the sub-cell coordinates in the edge words: points up to 16 units outside the cell stay representable
+constexpr int kGgSpan = 128 + 2 * kGgBias;     // biased coordinates lie in [0, kGgSpan)
+constexpr float kGgNorm = 100.0f;              // |a|, |b| <= kGgNorm: |a x + b y| <= 2 * 100 * 160 = 32000 < 255 * 127
+NLOS_HD int dp4a_s8_u8(unsigned a, unsigned b) {        // sum of the four signed bytes of a times the four unsigned bytes of b
+#if defined(__CUDA_ARCH__)
+  int d; asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0)); return d;
+#else
+  int d = 0;
+  for (int i = 0; i < 4; ++i) d += (int)(signed char)((a >> (8 * i)) & 0xffu) * (int)((b >> (8 * i)) & 0xffu);
+  return d;
+#endif
+}
+// projection of a scene point: picture coordinates, w = 1/Z, Z, relative round-off margin (as pg_project)
+NLOS_HD void gg_project(f3 o, f3 a, f3 b, f3 n, f3 x, float& u, float& v, float& w, float& z, float& m) {
+  const f3 rel = x - o;
+  z = dot3(rel, n);
+  w = pg_rcp(z);
+  u = dot3(rel, a) * w; v = dot3(rel, b) * w;
+  m = kPgPad * ((fabsf(rel.x) + fabsf(rel.y) + fabsf(rel.z)) * w);
+}
+NLOS_HD int gg_slice(const GGFrame& g, float w) { float t = (g.w1 - w) * g.sw; t = fminf(fmaxf(t, 0.0f), g.kmax); return (int)t; }   // monotone (decreasing) in w
+NLOS_HD int gg_fine(const GGFrame& g, float w, int k) {          // sub-slice of w inside slice k (clamped: w may lie in another slice)
+  float t = ((g.w1 - w) * g.sw - (float)k) * (float)kGgFine; t = fminf(fmaxf(t, 0.0f), (float)(kGgFine - 1)); return (int)t;
+}
+// one edge of a projected triangle, in the biased sub-cell units of a cell: (xa,ya)->(xb,yb) with (xc,yc) on the inner side.
+// ex, ey: how far (sub-cell units) the true picture point may be from the real-valued point the tested integer point was cut from.
+// Returns the edge word; 'never' is set when no point of the cell can satisfy the edge (the triangle misses the cell).
+NLOS_HD unsigned gg_edge_word(float xa, float ya, float xb, float yb, float xc, float yc, float ex, float ey, bool& never) {
+  float A = ya - yb, B = xb - xa;
+  float C = -fmaf(A, xa, B * ya);
+  const float side = fmaf(A, xc, fmaf(B, yc, C));
+  if (side < 0.0f) { A = -A; B = -B; C = -C; }
+  const float mx = fmaxf(fabsf(A), fabsf(B));
+  if (!(mx > 1.0e-20f) || !(mx < 1.0e20f)) return 0u;                     // degenerate in the picture: edge always passes (a = b = c = 0)
+  const float s = kGgNorm / mx;
+  const float fa = rintf(A * s), fb = rintf(B * s);
+  // slack: rounding of a, b (<= 0.5 each) over |x|, |y| <= span + e; distance of the tested integer point from the true one; float evaluation of C
+  const float slack = 0.5f * (((float)kGgSpan + 1.0f + ex) + ((float)kGgSpan + 1.0f + ey)) + fabsf(fa) * (1.0f + ex) + fabsf(fb) * (1.0f + ey) +
+                      1.0e-5f * s * (fabsf(A * xa) + fabsf(B * ya)) + 2.0f;
+  if (!(fabsf(side) * s > slack)) return 0u;                               // thinner than the slack (edge-on): orientation not certain, edge always passes
+  const float cf = C * s + slack;
+  if (!(cf < 32000.0f)) return 0u;                                         // (nearly) every point of the cell satisfies it: always passes
+  if (cf < -32100.0f) { never = true; return 0u; }
+  const int c = (int)ceilf(cf) + 1;
+  const int chi = (c >= 0 ? c + 127 : c - 127) / 255;
+  const int clo = c - 255 * chi;                                           // in [-127, 127]
+  return ((unsigned)(int)fa & 0xffu) | (((unsigned)(int)fb & 0xffu) << 8) | (((unsigned)chi & 0xffu) << 16) | (((unsigned)clo & 0xffu) << 24);
+}
+NLOS_HD bool gg_edges_pass(unsigned e0, unsigned e1, unsigned e2, unsigned rayword) {
+  return (dp4a_s8_u8(e0, rayword) | dp4a_s8_u8(e1, rayword) | dp4a_s8_u8(e2, rayword)) >= 0;
+}
+// quantisation, slices, slope bounds and expansions of a group's frame from the extent of its projected vertices
+// ([U0,U1] x [V0,V1] x [W0,W1], mm = largest round-off margin) and of its members (largest |delta.a|, |delta.b|, |delta.n|)
+NLOS_HD void gg_finish_frame(GGFrame& g, float U0, float U1, float V0, float V1, float W0, float W1, float mm,
+                             float max_da, float max_db, float max_dn, int G, int K) {
+  g.G = 0; g.K = K; g.kmax = (float)(K - 1);
+  if (G <= 0 || K <= 0 || !(U1 >= U0) || !(V1 >= V0) || !(W1 >= W0) || !(W0 > 0.0f) || !(mm < 1.0f)) return;
+  const float ua = fmaxf(fabsf(U0), fabsf(U1)), va = fmaxf(fabsf(V0), fabsf(V1));
+  g.pad_u = mm * (1.0f + ua); g.pad_v = mm * (1.0f + va);
+  g.pad_w = mm * W1;
+  g.dw = fmaxf((W1 - W0) + 2.0f * g.pad_w, 1.0e-30f) / (float)K;
+  g.sw = 1.0f / g.dw; g.w1 = W1 + g.pad_w;
+  g.Su = (max_da + max_dn * (2.0f * ua + 1.0f)) * 1.001f + 1.0e-12f;
+  g.Sv = (max_db + max_dn * (2.0f * va + 1.0f)) * 1.001f + 1.0e-12f;
+  g.eu = g.pad_u + g.Su * (0.5f * g.dw + 2.0f * g.pad_w); g.ev = g.pad_v + g.Sv * (0.5f * g.dw + 2.0f * g.pad_w);
+  U0 -= g.eu; U1 += g.eu; V0 -= g.ev; V1 += g.ev;
+  const float mu = 1.0e-3f * (U1 - U0) + 1.0e-6f, mv = 1.0e-3f * (V1 - V0) + 1.0e-6f;
+  U0 -= mu; U1 += mu; V0 -= mv; V1 += mv;
+  if (!(U1 - U0 < 3.0e30f) || !(V1 - V0 < 3.0e30f)) return;
+  const float Q = (float)(G << kPgSub);
+  g.u0 = U0; g.v0 = V0; g.su = Q / (U1 - U0); g.sv = Q / (V1 - V0); g.qmax = Q - 1.0f; g.G = G;
+}
+NLOS_HD void gg_coarsen(GGFrame& g) {        // halve the picture resolution (entry budget exceeded): same rectangle, coarser cells
+  const int G = g.G > 1 ? g.G >> 1 : 1;
+  const float k = (float)G / (float)g.G;
+  g.su *= k; g.sv *= k; g.G = G; g.qmax = (float)(G << kPgSub) - 1.0f;
+}
+// quantised, expanded rectangle and slice range of a triangle from its projected vertices (u, v, w); wlo / whi: its padded w range
+NLOS_HD void gg_tri_box(const GGFrame& g, float u1, float v1, float w1, float u2, float v2, float w2, float u3, float v3, float w3,
+                        int& a0, int& a1, int& b0, int& b1, int& k0, int& k1, float& wlo, float& whi) {
+  const float ulo = fminf(u1, fminf(u2, u3)) - g.eu, uhi = fmaxf(u1, fmaxf(u2, u3)) + g.eu;
+  const float vlo = fminf(v1, fminf(v2, v3)) - g.ev, vhi = fmaxf(v1, fmaxf(v2, v3)) + g.ev;
+  a0 = pg_quant(ulo, g.u0, g.su, g.qmax); a1 = pg_quant(uhi, g.u0, g.su, g.qmax);
+  b0 = pg_quant(vlo, g.v0, g.sv, g.qmax); b1 = pg_quant(vhi, g.v0, g.sv, g.qmax);
+  whi = fmaxf(w1, fmaxf(w2, w3)) + g.pad_w; wlo = fminf(w1, fminf(w2, w3)) - g.pad_w;
+  k0 = gg_slice(g, whi); k1 = gg_slice(g, wlo);
+}
+// fine depth index of a triangle's entry in slice k (middle sub-slice of its w range clipped to the slice) and the half width, in
+// sub-slices, of the w interval that index stands for
+NLOS_HD int gg_tri_fine(const GGFrame& g, float wlo, float whi, int k0, int k1, int k, float& half) {
+  const int ja = k > k0 ? 0 : gg_fine(g, whi, k), jb = k < k1 ? kGgFine - 1 : gg_fine(g, wlo, k);
+  const int jm = (ja + jb) >> 1;
+  half = 0.5f * (float)(jb - ja + 1) + 1.5f;            // the range itself, the middle's rounding, one sub-slice for the float assignment of ja / jb
+  return jm;
+}
+// the three edge words of a triangle in cell (cx, cy); half = largest gg_tri_fine() half width over the triangle's slices;
+// false: the triangle provably misses the cell
+NLOS_HD bool gg_tri_edges(const GGFrame& g, float u1, float v1, float u2, float v2, float u3, float v3, int cx, int cy, float half,
+                          unsigned& e0, unsigned& e1, unsigned& e2) {
+  const float bx = (float)((cx << kPgSub) - kGgBias), by = (float)((cy << kPgSub) - kGgBias);
+  const float x1 = (u1 - g.u0) * g.su - bx, y1 = (v1 - g.v0) * g.sv - by;
+  const float x2 = (u2 - g.u0) * g.su - bx, y2 = (v2 - g.v0) * g.sv - by;
+  const float x3 = (u3 - g.u0) * g.su - bx, y3 = (v3 - g.v0) * g.sv - by;
+  const float hw = half * g.dw * (1.0f / (float)kGgFine) + 2.0f * g.pad_w;
+  const float ex = (g.pad_u + g.Su * hw) * g.su, ey = (g.pad_v + g.Sv * hw) * g.sv;
+  bool never = false;
+  e0 = gg_edge_word(x1, y1, x2, y2, x3, y3, ex, ey, never);
+  e1 = gg_edge_word(x2, y2, x3, y3, x1, y1, ex, ey, never);
+  e2 = gg_edge_word(x3, y3, x1, y1, x2, y2, ex, ey, never);
+  return !never;
+}
+// the line of a ray in the group's projective space; false: the ray cannot use the grid (points away from the picture's half space,
+// or moves faster than the group's slope bound)
+struct GGRay { float ui, vi, su, sv; int kr; };
+NLOS_HD bool gg_ray_setup(const GGFrame& g, float da, float db, float dn /* delta in the frame */, f3 d, float ts, GGRay& r) {
+  const float zn = dot3(d, g.n);
+  if (!(zn > 0.0f)) return false;
+  const float rz = pg_rcp(zn);
+  r.ui = dot3(d, g.a) * rz; r.vi = dot3(d, g.b) * rz;
+  r.su = da - dn * r.ui; r.sv = db - dn * r.vi;
+  if (!(fabsf(r.su) <= g.Su) || !(fabsf(r.sv) <= g.Sv)) return false;
+  const float zh = fmaf(ts, zn, dn);
+  if (!(zh > 0.0f)) return false;
+  r.kr = gg_slice(g, pg_rcp(zh) - g.pad_w);
+  return true;
+}
+// the ray's walk through the slices: quantised picture coordinates (float, in sub-cell units of the whole picture) of the point at the
+// centre of slice k are  fu = au + k bu,  fv = av + k bv
+struct GGWalk { float au, bu, av, bv; };
+NLOS_HD GGWalk gg_ray_walk(const GGFrame& g, const GGRay& r) {
+  GGWalk w;
+  const float w0 = g.w1 - 0.5f * g.dw;
+  w.au = (fmaf(r.su, w0, r.ui) - g.u0) * g.su; w.bu = -(r.su * g.dw) * g.su;
+  w.av = (fmaf(r.sv, w0, r.vi) - g.v0) * g.sv; w.bv = -(r.sv * g.dw) * g.sv;
+  return w;
+}
+// quantised point of the walk in slice k (kf = (float)k): uq, vq in [0, Q-1]; the cell is (uq >> 7, vq >> 7)
+NLOS_HD void gg_walk_point(const GGFrame& g, const GGWalk& w, float kf, int& uq, int& vq) {
+  const float fu = fminf(fmaxf(fmaf(kf, w.bu, w.au), 0.0f), g.qmax), fv = fminf(fmaxf(fmaf(kf, w.bv, w.av), 0.0f), g.qmax);
+  uq = (int)fu; vq = (int)fv;
+}
+NLOS_HD unsigned gg_rect_word(int uq, int vq) {                  // rectangle check word of a quantised point (see pg_ray)
+  const unsigned su = (unsigned)(uq & 127), sv = (unsigned)(vq & 127);
+  return su - (su << 8) + (sv << 16) - (sv << 24);
+}
+// biased sub-cell coordinates of the walk's point at sub-slice 0 of slice k, and their change per sub-slice (edge check)
+struct GGFinePoint { float x0, y0, dx, dy; };
+NLOS_HD GGFinePoint gg_walk_fine(const GGWalk& w, float kf, int uq, int vq) {
+  GGFinePoint q;
+  q.dx = w.bu * (1.0f / (float)kGgFine); q.dy = w.bv * (1.0f / (float)kGgFine);
+  const float half = 0.5f * (float)(kGgFine - 1);
+  q.x0 = (fmaf(kf, w.bu, w.au) - (float)((uq & ~127) - kGgBias)) - half * q.dx;
+  q.y0 = (fmaf(kf, w.bv, w.av) - (float)((vq & ~127) - kGgBias)) - half * q.dy;
+  return q;
+}
+// edge check word of the ray at sub-slice j; false: the point left the representable range (the candidate then goes to the exact test)
+NLOS_HD bool gg_ray_word(const GGFinePoint& q, int j, unsigned& rayword) {
+  const int x = (int)floorf(fmaf((float)j, q.dx, q.x0)), y = (int)floorf(fmaf((float)j, q.dy, q.y0));
+  rayword = (unsigned)x | ((unsigned)y << 8) | 0x01ff0000u;
+  return (unsigned)x < (unsigned)kGgSpan && (unsigned)y < (unsigned)kGgSpan;
+}
+
 // ------------------------------------------------------------------ LBVH construction helpers (Karras 2012)
 NLOS_HD uint32_t expand_bits10(uint32_t v) {
   v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;

@@ -48,7 +48,10 @@ struct Ctx {
   int timing_enabled = 0;
   int chunk_forward = 0;         // sources per blockIdx.y in the forward pass (0 = auto)
   int chunk_gradient = 0;        // same for the gradient pass
-  int forward_algo = 0;          // 0 auto (perspective grid where it applies), 1 BVH traversal kernel, 2 perspective grid
+  int forward_algo = 0;          // 0 auto (shared perspective grid where it applies), 1 BVH traversal kernel, 2 per-wall-point perspective grid, 3 shared perspective grid
+  int group_side = 0;            // shared grid: a group is a tile of side x side wall spacings (0 = 4; 1 = one wall point per group)
+  int grid_slices = 0;           // shared grid: slices of 1/Z (0 = 16)
+  int grid_budget_mb = 0;        // shared grid: scratch memory for the lists of one batch of groups (0 = 6144 MiB)
   int grid_res = 0;              // cells per axis of the perspective grid (0 = auto from the triangle count)
   int count_work = 0;            // measurement: the next perspective-grid forward launch fills buf("work_counters") (nlos_ctx_get_work_counters)
   int work_G = 0;                // grid resolution of that launch

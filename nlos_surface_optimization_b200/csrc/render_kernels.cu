@@ -22,6 +22,7 @@
 #include <cmath>
 #include "nlos_ctx.h"
 #include "render_kernels.h"
+#include "group_grid.h"
 
 namespace nlos {
 #ifdef NLOS_EXT_BUILD      // second build of this file (render_kernels_ext.cu): the same kernels with the external-sample test hook compiled in
@@ -637,6 +638,254 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
   }
 }
 
+// ---------------------------------------------------------------------------------------------- K1s forward, shared perspective grid
+// The grid of k_forward_grid, built ONCE per group of neighbouring wall points (group_grid.cu, k_group_bin) instead of once per wall
+// point: seen from the group's centre the ray of a member wall point is a straight line of the projective space (u, v, 1/Z)
+// (nlos_core.cuh "shared perspective grid of a GROUP"), so the lists are 3-D — picture cell x slice of 1/Z — and a ray tests, slice by
+// slice up to the slice of its own hit, the list of the cell its line crosses there.  Nothing is built per wall point any more, so
+// nothing is shared between the warps of a block either: the unit of work is (wall point, run of triangles) per WARP, without any
+// block-level synchronisation.
+//   generate  lane <-> triangle as in k_forward_grid (plane-side cull, Philox, self intersection, shading); samples that can contribute
+//             are compacted into a per-warp ray queue (ballot + popc)
+//   trace     whenever 32 rays are queued: lane <-> ray.  Per slice: cell lookup (one 8-byte record), packed rectangle check of the
+//             list (4 entries per 16-byte load), survivors pooled over the warp for the exact test tri_occludes_od.  Visible rays add
+//             their value to the transient row (FP64 RED) and set their bit of the visibility word (RED.OR; the buffer is zeroed first).
+// The answer is the exact float test's, as before; rays that cannot use the grid (slope bound, wrong half space, group without grid)
+// take the per-ray BVH query.
+constexpr int kGrpBlock = 256;             // 8 warps
+constexpr int kGrpQ = 64;                  // ray queue slots per warp (a trace starts at 32 queued rays; one generate round adds at most 32)
+constexpr int kGrpPush = 8;                // candidates a lane hands to the warp's pool per round
+constexpr int kGrpFlush = 128;             // the pool is worked off when it holds more than this many candidates
+constexpr int kGrpPool = kGrpFlush + 32 * kGrpPush;
+struct GrpWarp {
+  float dx[kGrpQ], dy[kGrpQ], dz[kGrpQ], ts[kGrpQ], val[kGrpQ];
+  int bin[kGrpQ], tri[kGrpQ], prim[kGrpQ], kk[kGrpQ];   // histogram bin (-1: none), triangle (Morton index), triangle (caller's index), sample index of the slot
+  unsigned pool[kGrpPool];                 // work items of the exact tests: ray lane << 27 | candidate triangle
+  unsigned occ;                            // bit l: the ray of lane l is occluded
+  unsigned pad_[3];
+  GGFrame fr;                              // the group's frame (copied per work item)
+  unsigned pad2_[(128 - sizeof(GGFrame) % 128) / 4];
+};
+static_assert(sizeof(GrpWarp) % 16 == 0, "per-warp scratch must keep 16-byte alignment");
+
+// exact tests of the pooled candidates, all 32 lanes in the same loop
+__device__ __forceinline__ void group_work_pool(const DeviceScene& sc, GrpWarp& gw, f3 o, int qhead, int total, int lane) {
+  __syncwarp();
+  for (int i = lane; i < total; i += 32) {
+    const unsigned item = gw.pool[i];
+    const int rl = (int)(item >> 27);
+    if (!((gw.occ >> rl) & 1u)) {
+      const int rs = (qhead + rl) & (kGrpQ - 1);
+      const int tj = (int)(item & 0x7ffffffu);
+      if (tj != gw.tri[rs] && tri_occludes_od(sc.ttris, tj, o, mk3(gw.dx[rs], gw.dy[rs], gw.dz[rs]), gw.ts[rs], gw.prim[rs])) atomicOr(&gw.occ, 1u << rl);
+    }
+  }
+  __syncwarp();
+}
+
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE, bool COUNT>
+__device__ __forceinline__ void group_trace(const DeviceScene& sc, const RenderParams& P, double* __restrict__ out, uint32_t* __restrict__ vis,
+                                            const double* s_w, GrpWarp& gw, const GroupGrid& gg, bool grid, unsigned long long ent0, unsigned long long tab0,
+                                            f3 o, float da, float db, float dn, int64_t s, int qhead, int n, int lane, unsigned long long* counters) {
+  const int slot = (qhead + lane) & (kGrpQ - 1);
+  const bool has = lane < n;
+  const f3 d = mk3(gw.dx[slot], gw.dy[slot], gw.dz[slot]);
+  const float ts = gw.ts[slot];
+  const unsigned mytri = (unsigned)gw.tri[slot];
+  bool occ = false; int kr = -1; GGRay r;
+  r.ui = r.vi = r.su = r.sv = 0.f; r.kr = 0;
+  if (has) {
+    if (grid && gg_ray_setup(gw.fr, da, db, dn, d, ts, r)) kr = r.kr;
+    else occ = occluded(sc.nodes, sc.ttris, sc.root_count, make_ray(o, d), ts, gw.prim[slot]);
+  }
+  if (lane == 0) gw.occ = 0u;
+  __syncwarp();
+  const int G = gw.fr.G, K = gw.fr.K;
+  const uint4* __restrict__ ent = reinterpret_cast<const uint4*>(gg.ent) + 2 * (size_t)(ent0 >> 2);      // blocks of 4 entries: [E0 E1 E2 E3][T0 T1 T2 T3]
+  const unsigned lt = (1u << lane) - 1u;
+  const GGWalk wk = gg_ray_walk(gw.fr, r);
+  const uint2* __restrict__ tab = gg.table + tab0;
+  const float qmax = gw.fr.qmax;
+  unsigned nscan = 0u, nhit = 0u;
+  int np = 0;                                            // candidates waiting in the pool (warp-uniform)
+  int k = 0; float kf = 0.0f;                            // next slice of this lane's ray
+  for (;;) {
+    // every lane walks its ray to the next slice whose cell has a non-empty list (most lists a ray crosses are empty)
+    unsigned cnt = 0u, start = 0u; int uq = 0, vq = 0;
+    while (k <= kr && cnt == 0u) {
+      const float fu = fminf(fmaxf(fmaf(kf, wk.bu, wk.au), 0.0f), qmax), fv = fminf(fmaxf(fmaf(kf, wk.bv, wk.av), 0.0f), qmax);     // gg_walk_point
+      uq = (int)fu; vq = (int)fv;
+      const uint2 t = __ldg(tab + (unsigned)(((vq >> kPgSub) * G + (uq >> kPgSub)) * K + k));
+      start = t.x >> 2; cnt = t.y; ++k; kf += 1.0f;
+    }
+    const int ngrp = (int)((cnt + 3u) >> 2);
+    const int maxg = __reduce_max_sync(0xffffffffu, ngrp);
+    if (maxg == 0) break;
+    if (COUNT) nscan += 4u * (unsigned)ngrp;
+    const unsigned R = gg_rect_word(uq, vq);
+    const uint4* __restrict__ lst = ent + 2 * (size_t)start;
+    for (int g0 = 0; g0 < maxg; g0 += 8) {                                  // 32 entries per lane and round
+      unsigned mask = 0u;
+      if (g0 < ngrp) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (g0 + i < ngrp) {
+            const uint4 e = lst[2 * (g0 + i)];
+            if (pg_precheck(e.x, R)) mask |= 1u << (4 * i);
+            if (pg_precheck(e.y, R)) mask |= 2u << (4 * i);
+            if (pg_precheck(e.z, R)) mask |= 4u << (4 * i);
+            if (pg_precheck(e.w, R)) mask |= 8u << (4 * i);
+          }
+        }
+      }
+      if (COUNT) nhit += __popc(mask);
+      // survivors go to the warp's pool (up to kGrpPush per lane and round); the pool is worked off by all 32 lanes when it is full enough
+      while (__any_sync(0xffffffffu, mask != 0u)) {
+        const int nb = __popc(mask);
+        const int nn = nb < kGrpPush ? nb : kGrpPush;
+        int incl = nn;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += y; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int off = np + incl - nn;
+        for (int i = 0; i < nn; ++i) {
+          const int bpos = __ffs(mask) - 1; mask &= mask - 1u;
+          // the triangle words sit in the same 32-byte sector as the rectangle words just read
+          gw.pool[off + i] = ((unsigned)lane << 27) | (reinterpret_cast<const unsigned*>(lst + 2 * (g0 + (bpos >> 2)) + 1)[bpos & 3] & 0x7ffffffu);
+        }
+        np += total;
+        if (np > kGrpFlush) { group_work_pool(sc, gw, o, qhead, np, lane); np = 0; if ((gw.occ >> lane) & 1u) { mask = 0u; kr = -1; } }
+      }
+    }
+  }
+  if (np > 0) group_work_pool(sc, gw, o, qhead, np, lane);
+  __syncwarp();
+  occ = occ || ((gw.occ >> lane) & 1u);
+  const bool visible = has && !occ;
+  if (visible) {
+    const float val = gw.val[slot]; const int bin = gw.bin[slot];
+    const double dv = P.spp == 1 ? (double)val : (double)val / (double)P.spp;   // TG.cpp:231-232
+    if (MODE == 1) atomicAdd(out + gw.prim[slot], dv);
+    else if (bin >= 0) {
+      if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
+      else {
+        const int half = 2 * P.r_fwd * P.s_bin;
+        int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);
+        if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
+        for (int b = b0; b <= b1; ++b) {
+          int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
+          if (ihi > ilo) atomicAdd(out + s * P.numBins + b, dv * (s_w[ihi] - s_w[ilo]));
+        }
+      }
+    }
+    if (WRITE_VIS) atomicOr(vis + (size_t)(s * P.spp + gw.kk[slot]) * P.words_per_row + (mytri >> 5), 1u << (mytri & 31u));
+  }
+  if (COUNT) {                                                              // measurement instantiation only (bench.py roofline.executed)
+    const unsigned c1 = __reduce_add_sync(0xffffffffu, has ? 1u : 0u), c2 = __reduce_add_sync(0xffffffffu, nscan), c3 = __reduce_add_sync(0xffffffffu, nhit);
+    const unsigned c4 = __reduce_add_sync(0xffffffffu, visible ? 1u : 0u);
+    if (lane == 0) { atomicAdd(counters + 1, (unsigned long long)c1); atomicAdd(counters + 2, (unsigned long long)c2); atomicAdd(counters + 3, (unsigned long long)c3); atomicAdd(counters + 4, (unsigned long long)c4); }
+  }
+  __syncwarp();                                                             // the queue slots and gw.occ are reused by the next round
+}
+
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE, bool COUNT>
+__global__ void __launch_bounds__(kGrpBlock, 4) k_forward_group(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
+                                                    uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
+                                                    const GroupGrid gg, int chunk_batches, unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_w = reinterpret_cast<double*>(smem_raw);                                                  // SMOOTH: tap prefix sums
+  GrpWarp* gw_all = reinterpret_cast<GrpWarp*>(smem_raw + (SMOOTH ? (((size_t)(P.K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0));
+  if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += kGrpBlock) s_w[i] = wprefix[i]; __syncthreads(); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  GrpWarp& gw = gw_all[warp];
+  const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
+  const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
+  const int F = sc.F;
+  const unsigned lt = (1u << lane) - 1u;
+  const int nchunks = (F + 32 * chunk_batches - 1) / (32 * chunk_batches);
+  const int pos0 = __ldg(gg.gstart + gg.group0), npos = __ldg(gg.gstart + gg.group0 + gg.ngroups) - pos0;      // sorted wall positions of this batch
+  const int64_t n_items = (int64_t)npos * nchunks;
+  for (int64_t item = (int64_t)blockIdx.x * (kGrpBlock / 32) + warp; item < n_items; item += (int64_t)gridDim.x * (kGrpBlock / 32)) {
+    const int pos = pos0 + (int)(item / nchunks), chunk = (int)(item % nchunks);
+    const int64_t s = __ldg(gg.order + pos);
+    const GroupHdr* __restrict__ h = gg.hdr + (__ldg(gg.group_of + pos) - gg.group0);
+    __syncwarp();
+    if (lane < (int)(sizeof(GGFrame) / 4)) reinterpret_cast<unsigned*>(&gw.fr)[lane] = __ldg(reinterpret_cast<const unsigned*>(&h->fr) + lane);
+    const unsigned long long ent0 = h->ent0, tab0 = h->tab0;
+    const int nlive = h->nlive;
+    const int* __restrict__ live = gg.live + h->live0;
+    __syncwarp();
+    const bool grid = gw.fr.G > 0;
+    const f3 o = xyz(__ldg(P.origin + s)), on = xyz(__ldg(P.onormal + s));
+    const f3 del = o - gw.fr.o;
+    const float da = dot3(del, gw.fr.a), db = dot3(del, gw.fr.b), dn = dot3(del, gw.fr.n);
+    if (COUNT && lane == 0 && chunk == 0 && !grid) atomicAdd(counters + 5, 1ull);
+    int qhead = 0, qcount = 0;
+    // one generate step = one sample index of one batch of 32 triangles; the trace runs from a single call site whenever 32 rays are
+    // queued, and once more for the remainder when the item's triangles are used up
+    const int base0 = chunk * chunk_batches * 32;                      // position in the group's list of live triangles
+    if (base0 >= nlive) continue;
+    const int nb = min(chunk_batches, (nlive - base0 + 31) / 32);
+    int bi = 0, k = 0;
+    TriRegs t; t.prim = 0; bool culled = true; int p = 0;
+    for (;;) {
+      const bool more = bi < nb;
+      if (more) {
+        if (k == 0) {
+          const int li = base0 + bi * 32 + lane;
+          culled = true;
+          if (li < nlive) {
+            p = __ldg(live + li);
+            load_tri<HAS_VN, HAS_VA>(sc, p, t);
+            culled = false;
+            if (!HAS_VN && !P.sr) {                                   // same exact-safe plane-side cull as k_forward
+              const f3 w1 = t.st.v1 - o, w2 = t.st.v2 - o, w3 = t.st.v3 - o;
+              const float m1 = 1e-5f * (fabsf(w1.x) + fabsf(w1.y) + fabsf(w1.z));
+              culled = dot3(t.st.nf, w1) > m1 && dot3(on, w1) > m1 &&
+                       dot3(on, w2) > 1e-5f * (fabsf(w2.x) + fabsf(w2.y) + fabsf(w2.z)) &&
+                       dot3(on, w3) > 1e-5f * (fabsf(w3.x) + fabsf(w3.y) + fabsf(w3.z));
+            }
+          }
+        }
+        if (__all_sync(0xffffffffu, culled)) { ++bi; k = 0; continue; }
+        bool need = false; float val = 0.f, ts = 0.f; int bin = -1; f3 d = mk3(0.f, 0.f, 1.f);
+        if (!culled) {
+          SampleGeom g;
+          const TriRec trr = make_tri(t.st.v1, t.st.v2, t.st.v3);
+          if (draw_sample(P, P.src_offset + s, t.prim, k, o, t.st, trr, g) && g.r <= ub_half && g.r >= lb_half) {
+            const f3 n = shading_normal<HAS_VN>(t, g);
+            const float ff = -dot3(n, g.d) * dot3(on, g.d) / g.r / g.r;          // TG.cpp:224-227
+            if (P.sr ? ff != 0.0f : ff > 0.0f) {
+              const float alb = (MODE == 1) ? 1.0f : shading_albedo<HAS_VA>(t, g);
+              val = t.st.A * alb * ff * ff;
+              if (GGX) val = val * ggx_eval(P.alpha, dot3(n, -g.d));              // ggx/TG.cpp:236-238
+              if (MODE == 0) {
+                const int64_t b = (int64_t)floorf((2.0f * g.r - P.lb) / P.res_fwd);   // TG.cpp:229
+                bin = (b >= 0 && b < nbf) ? (int)b : -1;
+              }
+              need = true; d = g.d; ts = g.t;
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (COUNT) { const unsigned c0 = __reduce_add_sync(0xffffffffu, culled ? 0u : 1u); if (lane == 0) atomicAdd(counters, (unsigned long long)c0); }
+        if (need) {
+          const int q = (qhead + qcount + __popc(m & lt)) & (kGrpQ - 1);
+          gw.dx[q] = d.x; gw.dy[q] = d.y; gw.dz[q] = d.z; gw.ts[q] = ts; gw.val[q] = val; gw.bin[q] = bin; gw.tri[q] = p; gw.prim[q] = t.prim; gw.kk[q] = k;
+        }
+        qcount += __popc(m);
+        if (++k == P.spp) { k = 0; ++bi; }
+        __syncwarp();
+      }
+      if (qcount >= 32 || (!more && qcount > 0)) {
+        const int n = qcount < 32 ? qcount : 32;
+        group_trace<GGX, HAS_VN, HAS_VA, SMOOTH, WRITE_VIS, MODE, COUNT>(sc, P, out, vis, s_w, gw, gg, grid, ent0, tab0, o, da, db, dn, s, qhead, n, lane, counters);
+        qhead = (qhead + n) & (kGrpQ - 1); qcount -= n;
+      } else if (!more) break;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- K3 residual
 // diff = (data - T) [-> 2 d^3 if loss_flag] * weight      (SSG.cpp:543-550)
 __global__ void k_residual(const double* __restrict__ data, const double* __restrict__ weight, const double* __restrict__ T, double* __restrict__ diff, size_t n, int loss_flag) {
@@ -919,8 +1168,65 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   cx.launches += 1;
 }
 
+// shared-grid forward kernel: applies outside the first-generation mode, to any number of wall points (the unit of work is a warp)
+inline bool use_group_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
+  if (P.sr || sc.F < 1 || sc.F >= (1 << 27) || sc.V < 1 || P.L < 1 || P.L > 0x7fffffff || sc.bounds == nullptr || sc.verts == nullptr) return false;
+  return cx.forward_algo == 0 || cx.forward_algo == 3;
+}
+template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
+void launch_forward_group_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+  const int sms = cx.num_sms > 0 ? cx.num_sms : 148;
+  const int side = cx.group_side > 0 ? cx.group_side : 4;
+  const int n_groups = make_wall_groups(cx, P, side);
+  const int K = cx.grid_slices > 0 ? std::min(cx.grid_slices, 64) : 16;
+  int G = cx.grid_res > 0 ? cx.grid_res : (int)(std::sqrt((double)sc.F * std::min(P.spp, 16)) * 0.25 + 0.5);
+  G = std::max(1, std::min(G, 256));                                                       // quantised coordinates are 15-bit
+  while (G > 1 && (size_t)G * G * K > ((size_t)1 << 24)) --G;
+  const size_t tab = (size_t)G * G * K;
+  unsigned cap = (unsigned)(std::min<int64_t>((int64_t)10 * sc.F + 4 * (int64_t)tab + 1024, 0x7ffffff0) & ~(int64_t)3);
+  if (cx.grid_cap > 0) cap = (unsigned)std::max<int64_t>(std::min<int64_t>(cap, cx.grid_cap), ((int64_t)sc.F * K + 3 + 4 * K) & ~(int64_t)3);   // never below one coarsest-grid fill
+  const size_t per_group = (size_t)cap * 8 + tab * 8 + (size_t)sc.F * 4 + sizeof(GroupHdr);
+  const size_t budget = (size_t)(cx.grid_budget_mb > 0 ? cx.grid_budget_mb : 6144) << 20;
+  const int per_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_groups, budget / per_group));
+  cx.last_forward_algo = 3; cx.last_grid_res = G;
+  unsigned long long* counters = nullptr;
+  constexpr bool kCanCount = !GGX && !VN && !VA && MODE == 0;
+  const bool count = kCanCount && cx.count_work != 0;
+  if (cx.count_work) {
+    counters = cx.buf("work_counters").as<unsigned long long>(8);
+    NLOS_CUDA_OK(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), cx.stream));
+    cx.work_G = count ? G : 0;
+  }
+  if (vis) NLOS_CUDA_OK(cudaMemsetAsync(vis, 0, (size_t)P.L * P.spp * P.words_per_row * sizeof(uint32_t), cx.stream));      // visibility bits are OR-ed in
+  // triangles per work item: 64 batches of 32 (the rays left in the queue at the end of an item are traced with idle lanes), fewer when that would leave warps without work
+  const int64_t warps = (int64_t)sms * 4 * (kGrpBlock / 32);
+  int cb = 64;
+  while (cb > 1 && P.L * (((int64_t)sc.F + 32 * cb - 1) / (32 * cb)) < 4 * warps) cb >>= 1;
+  const size_t smem = (size_t)(kGrpBlock / 32) * sizeof(GrpWarp) + (SMOOTH ? (((size_t)(P.K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0);
+  for (int g0 = 0; g0 < n_groups; g0 += per_batch) {
+    const int ng = std::min(per_batch, n_groups - g0);
+    GroupGrid gg;
+    bin_wall_groups(cx, sc, P, g0, ng, n_groups, G, K, cap, !VN, gg);
+    gg.gstart = cx.buf("wg_start").as<int>((size_t)P.L + 1); gg.ngroups = ng;
+    const int blocks = sms * 4;
+#define NLOS_GROUP_LAUNCH(WV, CNT)                                                                                                              \
+  do {                                                                                                                                         \
+    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_group<GGX, VN, VA, SMOOTH, WV, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_forward_group<GGX, VN, VA, SMOOTH, WV, MODE, CNT><<<blocks, kGrpBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, gg, cb, counters);           \
+  } while (0)
+    if (count) {
+      if constexpr (kCanCount) { if (vis) NLOS_GROUP_LAUNCH(true, true); else NLOS_GROUP_LAUNCH(false, true); }
+    } else {
+      if (vis) NLOS_GROUP_LAUNCH(true, false); else NLOS_GROUP_LAUNCH(false, false);
+    }
+#undef NLOS_GROUP_LAUNCH
+    cx.launches += 1;
+  }
+}
+
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+  if (use_group_forward(cx, sc, P)) { launch_forward_group_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
   if (use_grid_forward(cx, sc, P)) { launch_forward_grid_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
   cx.last_forward_algo = 1; cx.last_grid_res = 0;
   const int64_t nchunks = (P.L * (int64_t)P.spp + P.chunk - 1) / P.chunk;
