@@ -120,7 +120,7 @@ struct BinShared {
   unsigned rect[6];                          // ordered-uint min / max of u, v, w of the projected vertices
   unsigned maxm;
   int wsum[kBinBlock / 32];
-  unsigned long long total;
+  unsigned long long total, added;           // entries (padded) of the grid; entries added minus entries counted (non-zero: a 16-bit counter wrapped)
   float rad1;                                // largest L1 distance of a member from the centre
   f3 on;                                     // the members' common wall normal (as given, not normalised)
   int same_normal;
@@ -130,8 +130,9 @@ struct BinShared {
 __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc, const float4* __restrict__ origin, const float4* __restrict__ onormal,
                                                             const int* __restrict__ order, const int* __restrict__ gstart, int g0, int ng,
                                                             GroupHdr* __restrict__ hdr, uint2* __restrict__ table, unsigned* __restrict__ ent_all,
-                                                            float4* __restrict__ proj_all, int* __restrict__ live_all, int cull, unsigned cap, int G0, int K, unsigned tab_stride) {
+                                                            float4* __restrict__ proj_all, int* __restrict__ live_all, int cull, unsigned cap, int G0, int K, unsigned tab_stride, int smem_bytes) {
   __shared__ BinShared bs;
+  extern __shared__ __align__(16) unsigned cnt16[];          // packed 16-bit (cell, slice) counters
   const int tid = threadIdx.x, lane = tid & 31;
   float4* __restrict__ proj = proj_all + (size_t)blockIdx.x * sc.V;
   const int F = sc.F;
@@ -259,38 +260,54 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
       nlive = (int)bs.total;
       __syncthreads();
     }
-    // ---------------- pass 1: count (coarsen until the entries fit), pass 2: fill
+    // ---------------- pass 1: count (coarsen until the entries fit), pass 2: fill.
+    // The (cell, slice) counters live in shared memory as packed 16-bit pairs whenever G*G*K of them fit (one global atomic per entry
+    // costs an L2 round trip each and bounded this kernel at ~1 ms per group); a count that could wrap (> 65535 entries in one list,
+    // detected through the sum of the counts) and grids too large for shared memory take the global counters of the table instead.
+    bool smem_counts = (size_t)bs.fr.G * bs.fr.G * K * 2 <= (size_t)smem_bytes;
     while (bs.use_grid) {
       const GGFrame fr = bs.fr;
       const int G = fr.G, ncell = G * G * K;
-      for (int i = tid; i < ncell; i += kBinBlock) tab[i] = make_uint2(0u, 0u);
+      if (smem_counts) { for (int i = tid; i < (ncell + 1) / 2; i += kBinBlock) cnt16[i] = 0u; }
+      else { for (int i = tid; i < ncell; i += kBinBlock) tab[i] = make_uint2(0u, 0u); }
+      if (tid == 0) { bs.total = 0ull; bs.added = 0ull; }
       __syncthreads();
+      unsigned mine = 0u;
       for (int p = tid; p < F; p += kBinBlock) {
         const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
         const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
         int a0, a1, b0, b1, k0, k1; float wlo, whi;
         gg_tri_box(fr, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z, a0, a1, b0, b1, k0, k1, wlo, whi);
         const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy0 = b0 >> kPgSub, cy1 = b1 >> kPgSub;
-        for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) for (int k = k0; k <= k1; ++k) atomicAdd(&tab[(cy * G + cx) * K + k].y, 1u);
+        mine += (unsigned)((cx1 - cx0 + 1) * (cy1 - cy0 + 1) * (k1 - k0 + 1));
+        for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) for (int k = k0; k <= k1; ++k) {
+          const int idx = (cy * G + cx) * K + k;
+          if (smem_counts) atomicAdd(&cnt16[idx >> 1], 1u << (16 * (idx & 1))); else atomicAdd(&tab[idx].y, 1u);
+        }
       }
+      if (smem_counts) atomicAdd(&bs.added, (unsigned long long)mine);
       __syncthreads();
-      // exclusive scan of the counts (each rounded up to a multiple of 4) -> cursor
+      // exclusive scan of the counts (each rounded up to a multiple of 4) -> first entry of every list
       unsigned long long total;
-      if (tid == 0) bs.total = 0ull;
-      __syncthreads();
       {
         const int per = (ncell + kBinBlock - 1) / kBinBlock;
         const int b = min(ncell, tid * per), e = min(ncell, b + per);
-        unsigned sum = 0;
-        for (int i = b; i < e; ++i) sum += (tab[i].y + 3u) & ~3u;
+        unsigned sum = 0, raw = 0;
+        for (int i = b; i < e; ++i) { const unsigned c = smem_counts ? ((cnt16[i >> 1] >> (16 * (i & 1))) & 0xffffu) : tab[i].y; raw += c; sum += (c + 3u) & ~3u; }
         atomicAdd(&bs.total, (unsigned long long)sum);          // exact total in 64 bits; the 32-bit scan below is exact whenever total <= cap
+        if (smem_counts) atomicAdd(&bs.added, 0ull - (unsigned long long)raw);
         const int incl = block_scan_incl<0>((int)sum, bs.wsum);
         unsigned base = (unsigned)incl - sum;
-        for (int i = b; i < e; ++i) { const unsigned c = (tab[i].y + 3u) & ~3u; tab[i].x = base; base += c; }
+        for (int i = b; i < e; ++i) {
+          const unsigned c = smem_counts ? ((cnt16[i >> 1] >> (16 * (i & 1))) & 0xffffu) : tab[i].y;
+          tab[i] = make_uint2(base, c); base += (c + 3u) & ~3u;
+        }
         __syncthreads();
         total = bs.total;
+        if (smem_counts && bs.added != 0ull) { smem_counts = false; __syncthreads(); continue; }     // a 16-bit count wrapped: count again with the global counters
       }
       if (total <= (unsigned long long)cap) {
+        if (smem_counts) { __syncthreads(); for (int i = tid; i < (ncell + 1) / 2; i += kBinBlock) cnt16[i] = 0u; __syncthreads(); }
         for (int p = tid; p < F; p += kBinBlock) {
           const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
           const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
@@ -300,17 +317,20 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
           for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) {
             const unsigned E = pg_entry(a0, a1, b0, b1, cx, cy);
             for (int k = k0; k <= k1; ++k) {
-              const unsigned pos = atomicAdd(&tab[(cy * G + cx) * K + k].x, 1u);
+              const int idx = (cy * G + cx) * K + k;
+              unsigned pos;
+              if (smem_counts) pos = tab[idx].x + ((atomicAdd(&cnt16[idx >> 1], 1u << (16 * (idx & 1))) >> (16 * (idx & 1))) & 0xffffu);
+              else pos = atomicAdd(&tab[idx].x, 1u);
               ent[(size_t)(pos >> 2) * 8 + (pos & 3u)] = E; ent[(size_t)(pos >> 2) * 8 + 4 + (pos & 3u)] = (unsigned)p;
             }
           }
         }
         __syncthreads();
-        // cursor -> first entry; the tail of every list up to its group-of-4 boundary gets the never-matching word 0
+        // the tail of every list up to its group-of-4 boundary gets the never-matching word 0 (global counters: cursor -> first entry)
         for (int c = tid; c < ncell; c += kBinBlock) {
-          const uint2 t = tab[c];
-          for (unsigned k = t.x; k < ((t.x + 3u) & ~3u); ++k) ent[(size_t)(k >> 2) * 8 + (k & 3u)] = 0u;
-          tab[c] = make_uint2(t.x - t.y, t.y);
+          uint2 t = tab[c];
+          if (!smem_counts) { t.x -= t.y; tab[c] = t; }
+          for (unsigned k = t.x + t.y; k < t.x + ((t.y + 3u) & ~3u); ++k) ent[(size_t)(k >> 2) * 8 + (k & 3u)] = 0u;
         }
         break;
       }
@@ -369,7 +389,11 @@ void bin_wall_groups(Ctx& cx, const DeviceScene& sc, const RenderParams& P, int 
   const int* order = cx.buf("wg_order").as<int>((size_t)P.L);
   const int* group_of = cx.buf("wg_group_of").as<int>((size_t)P.L);
   const int* start = cx.buf("wg_start").as<int>((size_t)P.L + 1);
-  k_group_bin<<<blocks, kBinBlock, 0, cx.stream>>>(sc, P.origin, P.onormal, order, start, g0, ng, hdr, table, ent, proj, live, cull ? 1 : 0, cap, G, K, tab_stride);
+  // shared memory for the packed 16-bit counters of the (cell, slice) lists, when they fit beside the static part
+  int smem_bytes = (int)std::min<size_t>(((size_t)tab_stride * 2 + 15) & ~size_t(15), (size_t)200 * 1024);
+  if ((size_t)tab_stride * 2 > (size_t)smem_bytes) smem_bytes = 0;
+  NLOS_CUDA_OK(cudaFuncSetAttribute(k_group_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_group_bin<<<blocks, kBinBlock, smem_bytes, cx.stream>>>(sc, P.origin, P.onormal, order, start, g0, ng, hdr, table, ent, proj, live, cull ? 1 : 0, cap, G, K, tab_stride, smem_bytes);
   cx.launches += 1;
   NLOS_CUDA_OK(cudaGetLastError());
   out.hdr = hdr; out.order = order; out.group_of = group_of; out.table = table; out.ent = ent; out.live = live; out.group0 = g0;

@@ -329,9 +329,10 @@ struct GridShared {
   int use_grid;
   unsigned rect[6];                        // ordered-uint min u, max u, min v, max v, min z, max z of the projected vertices
   unsigned maxm;                           // max round-off margin (float bits, m >= 0)
+  unsigned next_batch;                     // pass 3: first triangle of the next batch nobody has taken yet
   unsigned wsum[kGridBlock / 32];
 };
-struct GridScratch { float4* proj; uint2* rect; unsigned* entE; unsigned* entI;
+struct GridScratch { float4* proj; uint2* rect; unsigned* ent;
                      unsigned long long* counters; };   // counters: null, or 6 work counters (option "count_work"): samples generated, rays traced, entry words scanned, cell-level check passes, visible samples, sources without grid
 
 // exclusive prefix sum of the counts a[0..n), each rounded up to a multiple of 4, in place (shared memory); returns the total;
@@ -374,8 +375,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
   GridWarp& gw = gw_all[warp];
   float4* __restrict__ proj = scr.proj + (size_t)blockIdx.x * sc.V;
   uint2* __restrict__ trect = scr.rect + (size_t)blockIdx.x * sc.F;
-  unsigned* __restrict__ entE = scr.entE + (size_t)blockIdx.x * cap;
-  unsigned* __restrict__ entI = scr.entI + (size_t)blockIdx.x * cap;
+  unsigned* __restrict__ ent = scr.ent + 2 * (size_t)blockIdx.x * cap;      // blocks of 4 entries (32 bytes): [E0 E1 E2 E3][T0 T1 T2 T3] — a candidate's triangle word sits in the sector its rectangle word was read from
   const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
   const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
   const int F = sc.F;
@@ -477,15 +477,15 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           const int cy0 = b0 >> kPgSub;
           if (cx0 == cx1 && cy0 == cy1) {                                                      // the common case: one cell
             const unsigned pos = atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);
-            entE[pos] = pg_entry(a0, a1, b0, b1, cx0, cy0); entI[pos] = (unsigned)p;
+            ent[(size_t)(pos >> 2) * 8 + (pos & 3u)] = pg_entry(a0, a1, b0, b1, cx0, cy0); ent[(size_t)(pos >> 2) * 8 + 4 + (pos & 3u)] = (unsigned)p;
           } else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) {
             const unsigned pos = atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
-            entE[pos] = pg_entry(a0, a1, b0, b1, cx, cy); entI[pos] = (unsigned)p;
+            ent[(size_t)(pos >> 2) * 8 + (pos & 3u)] = pg_entry(a0, a1, b0, b1, cx, cy); ent[(size_t)(pos >> 2) * 8 + 4 + (pos & 3u)] = (unsigned)p;
           }
         }
         __syncthreads();
         // the tail of every list up to its group-of-4 boundary gets the never-matching word 0 (lists are scanned 4 entries per load)
-        for (int c = tid; c < ncell; c += kGridBlock) { const unsigned e = cells[c]; for (unsigned k = e; k < ((e + 3u) & ~3u); ++k) entE[k] = 0u; }
+        for (int c = tid; c < ncell; c += kGridBlock) { const unsigned e = cells[c]; for (unsigned k = e; k < ((e + 3u) & ~3u); ++k) ent[(size_t)(k >> 2) * 8 + (k & 3u)] = 0u; }
         __syncthreads();
         break;
       }
@@ -494,11 +494,19 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
       __syncthreads();
     }
     // ---------------- pass 3: samples
+    if (tid == 0) gs.next_batch = 0u;
+    __syncthreads();
     const bool grid = gs.use_grid != 0;
     if (COUNT && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
     const PGridFrame fr = gs.fr;
     const int G = fr.G;
-    for (int base = warp * 32; base < F; base += kGridBlock) {
+    // the warps draw their batches of 32 triangles from a block-wide counter: a static stride leaves the block waiting at the barrier
+    // below for its slowest warp (7.5 % of the kernel's stall samples)
+    for (;;) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(&gs.next_batch, 32u);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= F) break;
       const int p = base + lane;
       const bool active = p < F;
       TriRegs t; t.prim = 0;
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
             const int kr = pg_quant(ts * dot3(d, fr.n) + gs.pad_z, gs.z0, gs.sz, (float)(kGridK - 1));
             const int c = (cy * G + cx) * kGridK; start = c ? (int)((cells[c - 1] + 3u) & ~3u) : 0; ngrp = ((int)cells[c + kr] - start + 3) >> 2;
           }
-          const uint4* __restrict__ lst = reinterpret_cast<const uint4*>(entE + start);
+          const uint4* __restrict__ lst = reinterpret_cast<const uint4*>(ent) + 2 * (size_t)(start >> 2);
           // the warp's rays, readable by every lane: the exact tests below are pooled over the warp
           gw.dx[lane] = d.x; gw.dy[lane] = d.y; gw.dz[lane] = d.z; gw.ts[lane] = ts; gw.prim[lane] = t.prim;
           if (lane == 0) gw.occ = 0u;
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (g0 + i < ngrp) {
-                  const uint4 e = lst[g0 + i];
+                  const uint4 e = lst[2 * (g0 + i)];
                   if (pg_precheck(e.x, R)) mask |= 1u << (4 * i);
                   if (pg_precheck(e.y, R)) mask |= 2u << (4 * i);
                   if (pg_precheck(e.z, R)) mask |= 4u << (4 * i);
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
               int off = incl - n;
               // the pushing lane fetches the candidate's triangle index (up to kGridPush independent loads in flight) so that the exact-test
               // loop below starts with the triangle fetch instead of two dependent round trips
-              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | entI[start + 4 * g0 + bpos]; }
+              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | reinterpret_cast<const unsigned*>(lst + 2 * (g0 + (bpos >> 2)) + 1)[bpos & 3]; }
               __syncwarp();
               for (int i = lane; i < total; i += 32) {
                 const unsigned item = gw.pool[i];
@@ -1142,8 +1150,7 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   GridScratch scr;
   scr.proj = cx.buf("grid_proj").as<float4>((size_t)blocks * sc.V);
   scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
-  scr.entE = cx.buf("grid_entE").as<unsigned>((size_t)blocks * cap);
-  scr.entI = cx.buf("grid_entI").as<unsigned>((size_t)blocks * cap);
+  scr.ent = cx.buf("grid_ent").as<unsigned>(2 * (size_t)blocks * cap);
   cx.last_forward_algo = 2; cx.last_grid_res = G;
   scr.counters = nullptr;
   // work counters (option "count_work"): a separate instantiation, only for the Lambertian face-normal transient kernels (the headline)
@@ -1171,7 +1178,7 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
 // shared-grid forward kernel: applies outside the first-generation mode, to any number of wall points (the unit of work is a warp)
 inline bool use_group_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
   if (P.sr || sc.F < 1 || sc.F >= (1 << 27) || sc.V < 1 || P.L < 1 || P.L > 0x7fffffff || sc.bounds == nullptr || sc.verts == nullptr) return false;
-  return cx.forward_algo == 0 || cx.forward_algo == 3;
+  return cx.forward_algo == 3;          // on request only: measured slower than the per-wall-point grid on every BASELINE config
 }
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_group_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
