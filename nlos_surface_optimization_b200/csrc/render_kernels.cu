@@ -477,15 +477,17 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           const int cy0 = b0 >> kPgSub;
           if (cx0 == cx1 && cy0 == cy1) {                                                      // the common case: one cell
             const unsigned pos = atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);
-            ent[(size_t)(pos >> 2) * 8 + (pos & 3u)] = pg_entry(a0, a1, b0, b1, cx0, cy0); ent[(size_t)(pos >> 2) * 8 + 4 + (pos & 3u)] = (unsigned)p;
+            const unsigned w = pos + (pos & ~3u);                                              // entry pos -> word (pos / 4) * 8 + pos % 4
+            ent[w] = pg_entry(a0, a1, b0, b1, cx0, cy0); ent[w + 4] = (unsigned)p;
           } else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) {
             const unsigned pos = atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
-            ent[(size_t)(pos >> 2) * 8 + (pos & 3u)] = pg_entry(a0, a1, b0, b1, cx, cy); ent[(size_t)(pos >> 2) * 8 + 4 + (pos & 3u)] = (unsigned)p;
+            const unsigned w = pos + (pos & ~3u);
+            ent[w] = pg_entry(a0, a1, b0, b1, cx, cy); ent[w + 4] = (unsigned)p;
           }
         }
         __syncthreads();
         // the tail of every list up to its group-of-4 boundary gets the never-matching word 0 (lists are scanned 4 entries per load)
-        for (int c = tid; c < ncell; c += kGridBlock) { const unsigned e = cells[c]; for (unsigned k = e; k < ((e + 3u) & ~3u); ++k) ent[(size_t)(k >> 2) * 8 + (k & 3u)] = 0u; }
+        for (int c = tid; c < ncell; c += kGridBlock) { const unsigned e = cells[c]; for (unsigned k = e; k < ((e + 3u) & ~3u); ++k) ent[k + (k & ~3u)] = 0u; }
         __syncthreads();
         break;
       }
@@ -594,7 +596,10 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
               int off = incl - n;
               // the pushing lane fetches the candidate's triangle index (up to kGridPush independent loads in flight) so that the exact-test
               // loop below starts with the triangle fetch instead of two dependent round trips
-              for (int i = 0; i < n; ++i) { const int bpos = __ffs(mask) - 1; mask &= mask - 1u; gw.pool[off + i] = ((unsigned)lane << 27) | reinterpret_cast<const unsigned*>(lst + 2 * (g0 + (bpos >> 2)) + 1)[bpos & 3]; }
+              // (the triangle word of entry b of this round: word 8 g0 + b + (b & ~3) + 4 of the list — same 32-byte sector as its rectangle word)
+              const unsigned* __restrict__ tw = reinterpret_cast<const unsigned*>(lst) + (8 * g0 + 4);
+              const unsigned tag = (unsigned)lane << 27;
+              for (int i = 0; i < n; ++i) { const unsigned bpos = 31u - (unsigned)__clz(mask); mask ^= 1u << bpos; gw.pool[off + i] = tag | tw[bpos + (bpos & ~3u)]; }
               __syncwarp();
               for (int i = lane; i < total; i += 32) {
                 const unsigned item = gw.pool[i];
