@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 LB, UB, RES = 0.0, 1.44, 1.2e-3
 SAMPLE_NUM, REFINE, SIGMA = 20000, 10, 1
 WALL = 64
+FORWARD_KERNELS = {1: ('k_forward', 'BVH traversal'), 2: ('k_forward_grid', 'perspective grid per wall point, G=%d'),
+                   3: ('k_forward_group', 'perspective grid shared by groups of wall points (+ k_group_bin), G=%d')}   # nlos_ctx option forward_algo
 METRIC = 'transient path samples/sec (fwd+vertex grad)'
 UNIT = 'path samples/s'
 DTYPE = 'f32 math / f64 accumulation'
@@ -434,9 +436,8 @@ def roofline_record(env, p, phase, counters, ms_per_step, mb, sm_count, peaks, c
     samples = L * F * spp
     achieved = samples * fl_fwd / (fwd_ms * 1e-3) / 1e12
     peak, peak_how = mb.fp32(sm_count)
-    grid_used = counters.get('forward_algo', 0) == 2
     counted = counters.get('samples_generated', 0) > 0
-    rec = {'bound': 'fp32', 'kernel': 'k_forward_grid' if grid_used else 'k_forward', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+    rec = {'bound': 'fp32', 'kernel': FORWARD_KERNELS.get(counters.get('forward_algo', 0), ('k_forward', ''))[0], 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
            'peak_source': peak_how, 'kernel_ms': fwd_ms,
            'canonical': {'box_tests_per_path_sample': can['box_per_ray'], 'tri_tests_per_path_sample': can['tri_per_ray'], 'visible_fraction': rho,
                          'flops_per_path_sample': fl_fwd, 'counted_on': '%d path samples of 8 wall points of this workload, %.1f s (oracle.canonical_counts: Karras LBVH, one triangle per leaf, near child first, nearest hit)' % (can['rays'], can_s)},
@@ -518,7 +519,7 @@ def run_render_config(env, args, mb):
                        sc['label'], p['L'], (' of a %dx%d wall (weak scaling)' % (sc['wall'] * env.world, sc['wall'])) if (env.world > 1 and args.config != 'scale') else '',
                        ' + NCCL all-reduce' if env.world > 1 else ''),
                    'l2': 'flushed between timed iterations (256 MiB write)', 'ms_per_iteration': ms_per_step, 'wall_ms_per_step_incl_flush': 1e3 * t_wall / steps,
-                   'phase_ms': phase, 'visibility_reuse': True, 'forward_kernel': 'k_forward_grid (perspective grid, G=%d)' % counters['grid_res'] if counters.get('forward_algo', 0) == 2 else 'k_forward (BVH traversal)',
+                   'phase_ms': phase, 'visibility_reuse': True, 'forward_kernel': '%s (%s)' % tuple(x % counters['grid_res'] if '%d' in x else x for x in FORWARD_KERNELS.get(counters.get('forward_algo', 0), ('k_forward', 'BVH traversal'))),
                    'value_counts': '2*L*F*spp path samples per step (SURVEY 8d); the gradient pass reuses the forward visibility bits and traces no rays'},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }

@@ -59,8 +59,10 @@ int nlos_ctx_set_source_window(nlos_ctx* ctx, int64_t src_offset, int64_t num_so
 int nlos_ctx_wait_stream(nlos_ctx* ctx, void* stream);
 int nlos_ctx_signal_stream(nlos_ctx* ctx, void* stream);
 /* keys: "reuse_visibility" (1), "chunk_forward" (0 = auto), "chunk_gradient" (0 = auto), "timing" (0),
- *       "forward_algo" (0 = auto, 1 = BVH traversal kernel, 2 = per-source perspective-grid kernel), "grid_res" (0 = auto: cells per
- *       axis of the perspective grid), "grid_cap" (0 = none; test hook: entry budget of the grid per wall point), "count_work" (0) */
+ *       "forward_algo" (0 = auto, 1 = BVH traversal kernel, 2 = per-source perspective-grid kernel, 3 = perspective grid shared by
+ *       groups of neighbouring wall points), "grid_res" (0 = auto: cells per axis of the perspective grid), "grid_cap" (0 = none; test
+ *       hook: entry budget of the grid per wall point / group), "count_work" (0); shared grid only: "group_side" (0 = 4: a group is a tile
+ *       of side x side wall spacings), "grid_slices" (0 = 16 slices of 1/depth), "grid_budget_mb" (0 = 6144: scratch for one batch of groups) */
 int nlos_ctx_set_option(nlos_ctx* ctx, const char* key, int64_t value);
 /* ms of the last call: {scene build, forward, residual, gradient, total}; needs option "timing" = 1 */
 int nlos_ctx_get_timing(nlos_ctx* ctx, float* ms5);

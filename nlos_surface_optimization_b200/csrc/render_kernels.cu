@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
 //           (shared memory), the triangles whose rectangle overlaps it;  block scan -> offsets
 //           (entry budget exceeded -> halve the resolution and recount: no host round trip, the answer does not depend on G)
 //   pass 2  writes the cell lists into this block's slice of a global scratch buffer: 4-byte entry words (the rectangle clipped
-//           to the cell, four guarded bytes) and, in a parallel array, the triangle index
-//   pass 3  lane <-> triangle as in k_forward: draw the sample, self intersection, shading.  The samples of a warp that can
-//           contribute fall into a few neighbouring cells; the warp copies the entry words of that cell window into shared
-//           memory (coalesced, all loads in flight at once), every lane scans the list of ITS cell there with the packed
-//           pre-check (one add, one and, one compare per entry) and queues the survivors; the queued triangles then get the
-//           exact test tri_occludes_od with all lanes of the warp in the same loop.  No tree walk, no per-lane stack.
+//           to the cell, four guarded bytes) and the triangle index, in 32-byte blocks of four entries [E0 E1 E2 E3][T0 T1 T2 T3]
+//   pass 3  lane <-> triangle as in k_forward (the warps draw their batches of 32 triangles from a block-wide counter): draw the
+//           sample, self intersection, shading.  Every lane scans the list of ITS ray's cell (depth slices 0 .. slice of its own
+//           hit are contiguous) with the packed pre-check — one add, one and, one compare per entry, four entries per 16-byte
+//           load — and hands the survivors to the warp's pool; the pooled triangles then get the exact test tri_occludes_od with
+//           all lanes of the warp in the same loop.  No tree walk, no per-lane stack.
 // Visibility is still "no other triangle beats (t_self, prim)" over the exact float test — the grid only selects candidates,
 // conservatively (tests/emul/pgrid_emul.cpp checks the selection against the BVH query on every ray of C-bunny).
 // A source that does not see the whole mesh safely in front of it (a vertex with depth < zmin along the wall normal) falls

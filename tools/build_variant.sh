@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/../nlos_surface_optimization_b200/csrc"
 OUT=../../build/variants; mkdir -p $OUT/obj_$1
-for f in lbvh render_kernels render_kernels_ext mesh_kernels nlos_abi; do
+for f in lbvh group_grid render_kernels render_kernels_ext mesh_kernels nlos_abi; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -ccbin /usr/bin/g++ -Xptxas -v $2 -c $f.cu -o $OUT/obj_$1/$f.o 2> $OUT/obj_$1/$f.log &
 done
 wait

@@ -38,6 +38,11 @@ def run(algo, side=0, K=0, G=0, steps=3):
 
 T0, G0, w0, t0 = run(1)
 print('bvh        forward %.3f ms gradient %.3f total %.3f' % (t0['forward_ms'], t0['gradient_ms'], t0['total_ms']), flush=True)
+for a in sys.argv:
+    if a.startswith('--g2='):
+        for g in [int(x) for x in a[5:].split(',')]:
+            T1, G1, w1, t1 = run(2, 0, 0, g)
+            print('grid G=%3d  forward %.3f ms gradient %.3f total %.3f | words equal %s' % (g, t1['forward_ms'], t1['gradient_ms'], t1['total_ms'], np.array_equal(w0, w1)), flush=True)
 if '--no2' not in sys.argv:
     T1, G1, w1, t1 = run(2)
     print('grid       forward %.3f ms gradient %.3f total %.3f | words equal %s' % (t1['forward_ms'], t1['gradient_ms'], t1['total_ms'], np.array_equal(w0, w1)), flush=True)
