@@ -313,7 +313,7 @@ constexpr int kGridBlock = NLOS_GRID_BLOCK;
 #define NLOS_GRID_K 4
 #endif
 static_assert(NLOS_GRID_K == 1 || NLOS_GRID_K == 2 || NLOS_GRID_K == 4, "the slice index is packed into 2 bits");
-constexpr int kGridK = NLOS_GRID_K;           // depth slices per picture cell (1, 2 or 4): a ray only scans the slices up to its own depth
+constexpr int kGridK = NLOS_GRID_K;           // depth slices per picture cell at most (1, 2 or 4; the launcher passes the count Kz): a ray only scans the slices up to its own depth
 constexpr int kGridPush = 8;               // candidates a lane hands to the warp's work pool per round
 constexpr int kGridPool = 32 * kGridPush;  // (ray, candidate) work items per round
 struct GridWarp {                          // per-warp scratch of pass 3
@@ -361,10 +361,12 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned* a, int n, uns
   return total;
 }
 
-template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE, bool COUNT>
+// KZT: depth slices as a compile-time constant (kGridK: the common case, 2 % faster than the run-time count) or 0 = the run-time count Kz_arg
+template <bool GGX, bool HAS_VN, bool HAS_VA, bool SMOOTH, bool WRITE_VIS, int MODE, bool COUNT, int KZT>
 __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_grid(const DeviceScene sc, const RenderParams P, double* __restrict__ out,
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
-                                                    const GridScratch scr, unsigned cap, int G0) {
+                                                    const GridScratch scr, unsigned cap, int G0, int Kz_arg) {
+  const int Kz = KZT ? KZT : Kz_arg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GridShared& gs = *reinterpret_cast<GridShared*>(smem_raw);
   double* s_w = reinterpret_cast<double*>(smem_raw + ((sizeof(GridShared) + 15) & ~size_t(15)));                  // SMOOTH: tap prefix sums
@@ -426,14 +428,14 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
       gs.pad_u = mm * (1.0f + fmaxf(fabsf(U0), fabsf(U1))); gs.pad_v = mm * (1.0f + fmaxf(fabsf(V0), fabsf(V1)));
       pg_set_rect(gs.fr, U0 - gs.pad_u, U1 + gs.pad_u, V0 - gs.pad_v, V1 + gs.pad_v, G0);
       const float Z0 = ord2f(gs.rect[4]), Z1 = ord2f(gs.rect[5]);
-      gs.pad_z = 1.0e-5f * fabsf(Z1); gs.z0 = Z0; gs.sz = (float)kGridK / fmaxf(Z1 - Z0, 1.0e-30f);
+      gs.pad_z = 1.0e-5f * fabsf(Z1); gs.z0 = Z0; gs.sz = (float)Kz / fmaxf(Z1 - Z0, 1.0e-30f);
       if (gs.fr.G == 0) gs.use_grid = 0;
     }
     __syncthreads();
     // ---------------- pass 1: count (coarsen until the entries fit), then pass 2: fill
     while (gs.use_grid) {
       const PGridFrame fr = gs.fr; const float pad_u = gs.pad_u, pad_v = gs.pad_v, z0 = gs.z0, sz = gs.sz, pad_z = gs.pad_z;
-      const int G = fr.G, ncell = G * G * kGridK;
+      const int G = fr.G, ncell = G * G * Kz;
       for (int i = tid; i < ncell; i += kGridBlock) cells[i] = 0u;
       __syncthreads();
       // two-stage software pipeline: the vertex indices of triangle p + 2*stride and the projected vertices of p + stride are in
@@ -455,12 +457,12 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           int a0, a1, b0, b1;
           pg_tri_rect(fr, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, pad_u, pad_v, a0, a1, b0, b1);
           // depth slice of the triangle's nearest vertex: it can only occlude rays whose own hit is at least that deep
-          const int kz = pg_quant(fminf(p1.z, fminf(p2.z, p3.z)) - pad_z, z0, sz, (float)(kGridK - 1));
+          const int kz = pg_quant(fminf(p1.z, fminf(p2.z, p3.z)) - pad_z, z0, sz, (float)(Kz - 1));
           trect[p] = make_uint2((unsigned)a0 | ((unsigned)a1 << 16) | ((unsigned)(kz & 1) << 15) | ((unsigned)(kz >> 1) << 31), (unsigned)b0 | ((unsigned)b1 << 16));
           const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
           const int cy0 = b0 >> kPgSub;
-          if (cx0 == cx1 && cy0 == cy1) atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);       // the common case: one cell
-          else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+          if (cx0 == cx1 && cy0 == cy1) atomicAdd(&cells[(cy0 * G + cx0) * Kz + kz], 1u);       // the common case: one cell
+          else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cells[(cy * G + cx) * Kz + kz], 1u);
         }
       }
       __syncthreads();
@@ -476,11 +478,11 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           const int cx0 = a0 >> kPgSub, cx1 = a1 >> kPgSub, cy1 = b1 >> kPgSub;
           const int cy0 = b0 >> kPgSub;
           if (cx0 == cx1 && cy0 == cy1) {                                                      // the common case: one cell
-            const unsigned pos = atomicAdd(&cells[(cy0 * G + cx0) * kGridK + kz], 1u);
+            const unsigned pos = atomicAdd(&cells[(cy0 * G + cx0) * Kz + kz], 1u);
             const unsigned w = pos + (pos & ~3u);                                              // entry pos -> word (pos / 4) * 8 + pos % 4
             ent[w] = pg_entry(a0, a1, b0, b1, cx0, cy0); ent[w + 4] = (unsigned)p;
           } else for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) {
-            const unsigned pos = atomicAdd(&cells[(cy * G + cx) * kGridK + kz], 1u);
+            const unsigned pos = atomicAdd(&cells[(cy * G + cx) * Kz + kz], 1u);
             const unsigned w = pos + (pos & ~3u);
             ent[w] = pg_entry(a0, a1, b0, b1, cx, cy); ent[w + 4] = (unsigned)p;
           }
@@ -560,8 +562,8 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           int start = 0, ngrp = 0;
           if (in_picture) {
             // slices 0 .. kr of the ray's picture cell are contiguous: one scan range (the padding words between them never match)
-            const int kr = pg_quant(ts * dot3(d, fr.n) + gs.pad_z, gs.z0, gs.sz, (float)(kGridK - 1));
-            const int c = (cy * G + cx) * kGridK; start = c ? (int)((cells[c - 1] + 3u) & ~3u) : 0; ngrp = ((int)cells[c + kr] - start + 3) >> 2;
+            const int kr = pg_quant(ts * dot3(d, fr.n) + gs.pad_z, gs.z0, gs.sz, (float)(Kz - 1));
+            const int c = (cy * G + cx) * Kz; start = c ? (int)((cells[c - 1] + 3u) & ~3u) : 0; ngrp = ((int)cells[c + kr] - start + 3) >> 2;
           }
           const uint4* __restrict__ lst = reinterpret_cast<const uint4*>(ent) + 2 * (size_t)(start >> 2);
           // the warp's rays, readable by every lane: the exact tests below are pooled over the warp
@@ -1128,9 +1130,9 @@ inline dim3 sample_grid(const DeviceScene& sc, const RenderParams& P) {
 }
 
 // shared memory of k_forward_grid for a G x G grid
-inline size_t grid_smem_bytes(int G, bool smooth, int K) {
+inline size_t grid_smem_bytes(int G, int Kz, bool smooth, int K) {
   return ((sizeof(GridShared) + 15) & ~size_t(15)) + (smooth ? (((size_t)(K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0) +
-         (size_t)(kGridBlock / 32) * sizeof(GridWarp) + (size_t)G * G * kGridK * sizeof(unsigned);
+         (size_t)(kGridBlock / 32) * sizeof(GridWarp) + (size_t)G * G * Kz * sizeof(unsigned);
 }
 // perspective-grid forward kernel: applies outside the first-generation mode (its unclamped form factor traces rays behind the wall point)
 inline bool use_grid_forward(const Ctx& cx, const DeviceScene& sc, const RenderParams& P) {
@@ -1146,12 +1148,16 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   int G = cx.grid_res > 0 ? cx.grid_res : (int)(std::sqrt((double)sc.F * std::min(P.spp, 16)) * 0.25 + 0.5);   // ~16 samples per picture cell (measured optima: C-bunny G = 64, C-arm G = 16..32)
   if (G < 1) G = 1;
   if (G > 256) G = 256;                                                                  // quantised coordinates are 15-bit
-  while (G > 1 && grid_smem_bytes(G, SMOOTH, P.K) > budget) --G;
-  const size_t smem = grid_smem_bytes(G, SMOOTH, P.K);
+  // depth slices: kGridK (4) while the wanted resolution fits shared memory with them, else fewer slices for a finer picture (the cell
+  // counters are G*G*Kz words).  Measured on the C-scale mesh (F = 500 000, wanted G = 177): Kz = 4 / G = 105 207 ms, 2 / 148 185 ms, 1 / 177 156 ms
+  int Kz = cx.grid_slices > 0 ? std::min(cx.grid_slices, kGridK) : kGridK;
+  if (cx.grid_slices <= 0) while (Kz > 1 && grid_smem_bytes(G, Kz, SMOOTH, P.K) > budget) Kz >>= 1;
+  while (G > 1 && grid_smem_bytes(G, Kz, SMOOTH, P.K) > budget) --G;
+  const size_t smem = grid_smem_bytes(G, Kz, SMOOTH, P.K);
   const int blocks = (int)std::min<int64_t>(P.L, (int64_t)sms * NLOS_GRID_MINBLOCKS);
-  const unsigned cap = (unsigned)(std::min<int64_t>((int64_t)6 * sc.F + 4 * (int64_t)G * G * kGridK + 1024, 0x7fffff0) & ~(int64_t)3);     // entry positions are 27-bit, lists 16-byte aligned
+  const unsigned cap = (unsigned)(std::min<int64_t>((int64_t)6 * sc.F + 4 * (int64_t)G * G * Kz + 1024, 0x7fffff0) & ~(int64_t)3);     // entry positions are 27-bit, lists 16-byte aligned
   unsigned capv = cap;
-  if (cx.grid_cap > 0) capv = (unsigned)std::max<int64_t>(std::min<int64_t>(cap, cx.grid_cap), ((int64_t)sc.F + 3 + 4 * kGridK) & ~(int64_t)3);   // never below one coarsest-grid fill
+  if (cx.grid_cap > 0) capv = (unsigned)std::max<int64_t>(std::min<int64_t>(cap, cx.grid_cap), ((int64_t)sc.F + 3 + 4 * Kz) & ~(int64_t)3);   // never below one coarsest-grid fill
   GridScratch scr;
   scr.proj = cx.buf("grid_proj").as<float4>((size_t)blocks * sc.V);
   scr.rect = cx.buf("grid_rect").as<uint2>((size_t)blocks * sc.F);
@@ -1168,8 +1174,13 @@ void launch_forward_grid_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P
   }
 #define NLOS_GRID_LAUNCH(WV, CNT)                                                                                                              \
   do {                                                                                                                                         \
-    NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G);           \
+    if (Kz == kGridK) {                                                                                                                        \
+      NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT, kGridK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT, kGridK><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G, Kz);   \
+    } else {                                                                                                                                   \
+      NLOS_CUDA_OK(cudaFuncSetAttribute(k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_forward_grid<GGX, VN, VA, SMOOTH, WV, MODE, CNT, 0><<<blocks, kGridBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix, scr, capv, G, Kz);        \
+    }                                                                                                                                          \
   } while (0)
   if (count) {
     if constexpr (kCanCount) { if (vis) NLOS_GRID_LAUNCH(true, true); else NLOS_GRID_LAUNCH(false, true); }

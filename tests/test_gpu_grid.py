@@ -52,6 +52,22 @@ def test_grid_resolution_and_coarsening_do_not_change_the_answer(gres, gcap, ctx
     assert rel_l2(T2, T1) <= 1e-12
 
 
+@pytest.mark.parametrize('slices', [1, 2, 3])
+def test_fewer_depth_slices_do_not_change_the_answer(slices, ctx):
+    """Large meshes trade depth slices for picture resolution (the cell counters must fit shared memory): any slice count gives the same bits."""
+    from nlos_surface_optimization_b200 import scenes
+    o, n = scenes.wall_grid(6); v, f = scenes.bunny(); ns = 20000
+    data = np.zeros((o.shape[0], 1200)); weight = np.ones_like(data)
+    T1, G1, w1 = _grad(ctx, o, n, v, f, ns, data, weight, 1)
+    ctx.set_option('grid_slices', slices)
+    try:
+        T2, G2, w2 = _grad(ctx, o, n, v, f, ns, data, weight, 2)
+    finally:
+        ctx.set_option('grid_slices', 0)
+    assert np.array_equal(w1, w2)
+    assert rel_l2(T2, T1) <= 1e-12
+
+
 def test_grid_with_tilted_and_unnormalised_wall_normals(oracle, ctx):
     from nlos_surface_optimization_b200 import scenes, renderer
     o, n = scenes.wall_grid(6)
