@@ -70,7 +70,7 @@ uint64_t nlos_ctx_launch_count(nlos_ctx* ctx);         /* kernels launched throu
 /* MEASUREMENT: with option "count_work" = 1 the perspective-grid forward kernel counts its own work; after the call out8 holds
  * {samples generated (not plane-culled), rays traced, entry words scanned, cell-level check passes (= exact-test candidates incl. self),
  *  visible samples, wall points handled without a grid, grid resolution G of the last forward launch, its kernel (1 = BVH traversal,
- *  2 = perspective grid)}; the first six are zero unless the counting instantiation ran (Lambertian, face normals).  bench.py prices
+ *  2 = perspective grid per wall point, 3 = perspective grid shared by groups of wall points)}; the first six are zero unless the counting instantiation ran (Lambertian, face normals).  bench.py prices
  *  roofline.executed with them. */
 int nlos_ctx_get_work_counters(nlos_ctx* ctx, uint64_t* out8);
 /* TEST HOOK (no reference counterpart): replace the counter-based generator by an external stream of (S,T) pairs, n floats (host or

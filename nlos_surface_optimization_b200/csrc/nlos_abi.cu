@@ -5,6 +5,7 @@
 //   ggx/stratifiedStreamedTransientRenderer.cpp, ggx/stratifiedStreamedGradientRenderer.cpp:27-239
 // Per call: stage inputs -> K0 scene build -> K1 forward (+visibility bits) -> K3 residual -> K4/K5
 // gradient -> finalize -> copy results back.  No CPU compute path exists in this library.
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around the phases of a call (visible to profilers, no-ops otherwise)
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -198,11 +199,13 @@ void run_job(Ctx& cx, const Job& j_in) {
   DeviceScene sc;
   if (j.F > 0 && j.L > 0) {
     // ---- K0: scene
+    nvtxRangePushA("nlos: scene build");
     build_scene(cx, d_verts, j.V, d_faces, j.F, d_origin, j.L, d_vn, d_va, sc);
     float4* origin4 = cx.buf("origin4").as<float4>((size_t)j.L);
     float4* onormal4 = cx.buf("onormal4").as<float4>((size_t)j.L);
     launch_pack4(cx, d_origin, origin4, (size_t)j.L);
     launch_pack4(cx, d_onormal, onormal4, (size_t)j.L);
+    nvtxRangePop();
     if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[1], st));
 
     RenderParams P;
@@ -240,6 +243,7 @@ void run_job(Ctx& cx, const Job& j_in) {
       if (timing) { NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[4], st)); }
     } else {
       // ---- K1: forward (+ visibility bits for the gradient pass)
+      nvtxRangePushA("nlos: forward");
       uint32_t* vis = nullptr;
       const bool want_grad = j.kind >= 0 && j.kind <= 2;
       cx.vis_words = 0;
@@ -261,10 +265,12 @@ void run_job(Ctx& cx, const Job& j_in) {
         launch_jitter_conv(cx, hist, d_jw, j.jlen, j.joff, j.numBins, j.L, o_T.dev);
       } else
       fwd(cx, sc, P, j.ggx, o_T.dev, vis, d_wprefix);
+      nvtxRangePop();
       if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[2], st));
       NLOS_CUDA_OK(cudaEventRecord(cx.ev_fwd, st)); fwd_recorded = true;        // the transient is final here
       if (want_grad) {
         // ---- K3: residual
+        nvtxRangePushA("nlos: residual + gradient");
         // host data/weight ride the copy stream while the forward kernel (already enqueued) runs
         const double* d_data = stage_in(cx, "in_data", j.data, LB, cx.copy_stream);
         const double* d_weight = j.weight ? stage_in(cx, "in_weight", j.weight, LB, cx.copy_stream) : nullptr;
@@ -303,6 +309,7 @@ void run_job(Ctx& cx, const Job& j_in) {
           NLOS_CUDA_OK(cudaStreamSynchronize(st));
           if (j.scalar_out) *j.scalar_out = h / (double)Lnorm;                           // TG.cpp:494-498
         }
+        nvtxRangePop();
         if (timing) NLOS_CUDA_OK(cudaEventRecord(cx.ev[4], st));
       } else if (timing) { NLOS_CUDA_OK(cudaEventRecord(cx.ev[3], st)); NLOS_CUDA_OK(cudaEventRecord(cx.ev[4], st)); }
     }
