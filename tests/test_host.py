@@ -237,3 +237,32 @@ def test_sharded_gradient_allreduce_gloo_world2(oracle, tmp_path):
         out = np.load(str(tmp_path / ('out%d.npz' % r)))
         assert rel_l2(out['T'], T_ref) < 1e-14
         assert rel_l2(out['G'], G_ref) < 1e-10
+
+
+@pytest.fixture(scope='module')
+def ggrid():
+    d = os.path.join(ROOT, 'tests', 'emul')
+    so = os.path.join(d, 'libggrid.so')
+    src = os.path.join(d, 'ggrid_emul.cpp')
+    core = os.path.join(ROOT, 'nlos_surface_optimization_b200', 'csrc', 'nlos_core.cuh')
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+        subprocess.check_call([cxx, '-O2', '-std=c++17', '-fopenmp', '-fPIC', '-ffp-contract=off', '-I/usr/local/cuda/include', '-shared', '-o', so, src])
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize('mesh,wall,G,K,gx,gy', [('bunny', 8, 66, 16, 4, 4), ('bunny', 8, 40, 8, 2, 2), ('bunny', 6, 66, 4, 1, 1), ('armadillo_init', 8, 16, 4, 4, 4)])
+def test_shared_grid_selection_on_host_never_misses_an_occluder(mesh, wall, G, K, gx, gy, ggrid):
+    """The candidate selection of the shared perspective grid (nlos_core.cuh gg_*: group frame, 3-D binning, slice walk, rectangle
+    words, fine depth index and edge words) compiled for the host: the visibility answer over the selected candidates equals the BVH
+    any-hit query for every traced ray."""
+    from nlos_surface_optimization_b200 import scenes
+    o, n = scenes.wall_grid(wall); v, f = getattr(scenes, mesh)()
+    out = np.zeros(16)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    rc = ggrid.ggrid_emul(fp(o), fp(n), o.shape[0], fp(v), v.shape[0], f.ctypes.data_as(C.POINTER(C.c_int)), f.shape[0], G, K, wall, gx, gy, 1,
+                          out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    rays, mismatches, fallback, nogrid = out[0], out[8], out[10], out[12]
+    assert rays > 1000 and mismatches == 0 and nogrid == 0
+    assert out[7] < out[5]          # the edge words remove candidates: exact tests per ray < rectangle survivors per ray
