@@ -36,4 +36,17 @@ renderer_sr.renderStreamedGradient(o, n, v, f, ns, lb, ub, res, 3, T, pl, G, dat
 ro = np.tile(o, (8, 1)).astype(np.float32); rd = np.tile(np.array([[0.02, -0.04, 1.0]], np.float32), (ro.shape[0], 1))
 bc = np.zeros((ro.shape[0], 3), np.float32); embree_intersector.embree3_tbb_intersection(ro, rd, v, f, bc)
 pw = np.zeros((ro.shape[0], 3), np.float32); embree_intersector.barycoord_to_world(v, f, bc, pw)
-print('sanitize run ok', T.sum(), np.abs(G).sum(), vis.mean())
+# the two grid forward kernels (the auto choice above is the BVH kernel: 9 wall points < SMs): per-point grid with 4, 2, 1 depth slices and
+# through its coarsening path; shared grid (wall grouping, binning kernel with shared-memory and with global counters, live lists, batches)
+o2, n2 = scenes.wall_grid(5); L2 = o2.shape[0]
+T2 = np.zeros((L2, B)); d2 = np.zeros((L2, B)); w2 = np.ones((L2, B))
+for algo, opts in ((2, {}), (2, {'grid_slices': 2}), (2, {'grid_slices': 1}), (2, {'grid_res': 40, 'grid_cap': 700}),
+                   (3, {}), (3, {'group_side': 2, 'grid_slices': 4}), (3, {'grid_res': 200, 'grid_slices': 16}), (3, {'grid_budget_mb': 1}), (3, {'grid_res': 40, 'grid_cap': 2000})):
+    ctx.set_option('forward_algo', algo)
+    for k_, v_ in opts.items(): ctx.set_option(k_, v_)
+    renderer.renderStreamedGradient(o2, n2, v, f, ns, lb, ub, res, T2, pl, G, d2, w2, 10, 1, 1, 0, ctx=ctx)
+    renderer.renderStreamedTransient(o2, n2, v, f, ns, lb, ub, res, T2, pl, 10, 1, ctx=ctx)
+    ggx.renderStreamedGradient(o2, n2, v, f, 0.3, ns, lb, ub, res, T2, pl, G, d2, w2, 10, 1, 1, ctx=ctx)
+    for k_ in opts: ctx.set_option(k_, 0)
+ctx.set_option('forward_algo', 0)
+print('sanitize run ok', T.sum(), np.abs(G).sum(), vis.mean(), T2.sum())
