@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kFwdBlock, NLOS_FWD_MINBLOCKS) k_forward(const
               // Gaussian smoothing + downsampling of TG.cpp:348-371 applied per sample: tap i of fine bin m lands in
               // coarse bin floor((m + i - 2rs)/r); the taps of one coarse bin are a contiguous run -> prefix sums
               const int half = 2 * P.r_fwd * P.s_bin;
-              int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);      // bin < numBins * r_fwd < 2^31
+              const int q0 = floordiv32(bin, P.r_fwd); int b0 = q0 - 2 * P.s_bin, b1 = q0 + 2 * P.s_bin;      // half = 2 r s is a multiple of r: one division (bin < numBins * r_fwd < 2^31)
               if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
               for (int b = b0; b <= b1; ++b) {
                 int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
             if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
             else {
               const int half = 2 * P.r_fwd * P.s_bin;
-              int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);
+              const int q0 = floordiv32(bin, P.r_fwd); int b0 = q0 - 2 * P.s_bin, b1 = q0 + 2 * P.s_bin;      // half = 2 r s is a multiple of r: one division
               if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
               for (int b = b0; b <= b1; ++b) {
                 int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
@@ -785,7 +785,7 @@ __device__ __forceinline__ void group_trace(const DeviceScene& sc, const RenderP
       if (!SMOOTH) atomicAdd(out + s * P.numBins + bin, dv);
       else {
         const int half = 2 * P.r_fwd * P.s_bin;
-        int b0 = floordiv32(bin - half, P.r_fwd), b1 = floordiv32(bin + half, P.r_fwd);
+        const int q0 = floordiv32(bin, P.r_fwd); int b0 = q0 - 2 * P.s_bin, b1 = q0 + 2 * P.s_bin;      // half = 2 r s is a multiple of r: one division
         if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
         for (int b = b0; b <= b1; ++b) {
           int ilo, ihi; tap_span32(bin, b, P.r_fwd, half, P.K, ilo, ihi);
@@ -988,14 +988,26 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
         const double x = ((double)(2.0f * hl) - (double)P.lb) * P.inv_res_fine;
         if (!(x > -1.0e9 && x < 1.0e9)) continue;                     // no tap of such a sample lands in [0, numBins); keeps the rest in 32 bits
         const int m0 = (int)floor(x);
-        int b0 = floordiv32(m0 - half, P.r_grad), b1 = floordiv32(m0 + half, P.r_grad);
+        // coarse bins the taps of fine bin m0 reach: floor((m0 -+ half) / r) with half = 2 r s a multiple of r -> ONE division
+        const int q0 = floordiv32(m0, P.r_grad);
+        int b0 = q0 - 2 * P.s_bin, b1 = q0 + 2 * P.s_bin;
         if (b0 < 0) b0 = 0; if (b1 > P.numBins - 1) b1 = P.numBins - 1;
         const double* drow = diff + s * P.numBins;
-        for (int b = b0; b <= b1; ++b) {
-          int ilo, ihi; tap_span32(m0, b, P.r_grad, half, P.K, ilo, ihi);
-          const double df = __ldg(drow + b);
-          At += (s_w[ihi] - s_w[ilo]) * df;
-          Bt += (s_d[ihi] - s_d[ilo]) * df;
+        if (b0 <= b1) {
+          // the tap run of coarse bin b is [ilo, ihi) = clamp(b r - m0 + half + {0, r}, 0, K) (tap_span32): the upper end of one bin is
+          // the lower end of the next, so every prefix-table entry is read once
+          int lo = b0 * P.r_grad - m0 + half;
+          int i0 = lo < 0 ? 0 : (lo > P.K ? P.K : lo);
+          double w0 = s_w[i0], d0 = s_d[i0];
+          for (int b = b0; b <= b1; ++b) {
+            lo += P.r_grad;
+            const int i1 = lo < 0 ? 0 : (lo > P.K ? P.K : lo);
+            const double w1 = s_w[i1], d1 = s_d[i1];
+            const double df = __ldg(drow + b);
+            At += (w1 - w0) * df;
+            Bt += (d1 - d0) * df;
+            w0 = w1; d0 = d1;
+          }
         }
         At *= -2.0; Bt *= -2.0;
       }
@@ -1038,13 +1050,18 @@ __global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const
         const float fa = (float)At;
         const float fb = (float)((double)inten * P.grad_coef * Bt);
         const float sA = t.st.A;
-        f3 gk;
-        gk = (t1 * g.u + cross3(t2, e1)) * fa + d * (g.u * fb);
-        g1x += (double)(sA * gk.x) * inv_spp; g1y += (double)(sA * gk.y) * inv_spp; g1z += (double)(sA * gk.z) * inv_spp;
-        gk = (t1 * g.v + cross3(t2, e2)) * fa + d * (g.v * fb);
-        g2x += (double)(sA * gk.x) * inv_spp; g2y += (double)(sA * gk.y) * inv_spp; g2z += (double)(sA * gk.z) * inv_spp;
-        gk = (t1 * g.w + cross3(t2, e3)) * fa + d * (g.w * fb);
-        g3x += (double)(sA * gk.x) * inv_spp; g3y += (double)(sA * gk.y) * inv_spp; g3z += (double)(sA * gk.z) * inv_spp;
+        const f3 gk1 = (t1 * g.u + cross3(t2, e1)) * fa + d * (g.u * fb);
+        const f3 gk2 = (t1 * g.v + cross3(t2, e2)) * fa + d * (g.v * fb);
+        const f3 gk3 = (t1 * g.w + cross3(t2, e3)) * fa + d * (g.w * fb);
+        if (P.spp == 1) {                                               // x * (1.0 / 1) == x: nine FP64 multiplies less per visible sample
+          g1x += (double)(sA * gk1.x); g1y += (double)(sA * gk1.y); g1z += (double)(sA * gk1.z);
+          g2x += (double)(sA * gk2.x); g2y += (double)(sA * gk2.y); g2z += (double)(sA * gk2.z);
+          g3x += (double)(sA * gk3.x); g3y += (double)(sA * gk3.y); g3z += (double)(sA * gk3.z);
+        } else {
+          g1x += (double)(sA * gk1.x) * inv_spp; g1y += (double)(sA * gk1.y) * inv_spp; g1z += (double)(sA * gk1.z) * inv_spp;
+          g2x += (double)(sA * gk2.x) * inv_spp; g2y += (double)(sA * gk2.y) * inv_spp; g2z += (double)(sA * gk2.z) * inv_spp;
+          g3x += (double)(sA * gk3.x) * inv_spp; g3y += (double)(sA * gk3.y) * inv_spp; g3z += (double)(sA * gk3.z) * inv_spp;
+        }
       }
     }
   }
