@@ -314,7 +314,10 @@ constexpr int kGridBlock = NLOS_GRID_BLOCK;
 #endif
 static_assert(NLOS_GRID_K == 1 || NLOS_GRID_K == 2 || NLOS_GRID_K == 4, "the slice index is packed into 2 bits");
 constexpr int kGridK = NLOS_GRID_K;           // depth slices per picture cell at most (1, 2 or 4; the launcher passes the count Kz): a ray only scans the slices up to its own depth
-constexpr int kGridPush = 8;               // candidates a lane hands to the warp's work pool per round
+#ifndef NLOS_GRID_PUSH
+#define NLOS_GRID_PUSH 8
+#endif
+constexpr int kGridPush = NLOS_GRID_PUSH;   // candidates a lane hands to the warp's work pool per round
 constexpr int kGridPool = 32 * kGridPush;  // (ray, candidate) work items per round
 struct GridWarp {                          // per-warp scratch of pass 3
   float dx[32], dy[32], dz[32], ts[32]; int prim[32];   // the warp's rays, readable by every lane
