@@ -507,13 +507,17 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
     if (COUNT && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
     const PGridFrame fr = gs.fr;
     const int G = fr.G;
-    // the warps draw their batches of 32 triangles from a block-wide counter: a static stride leaves the block waiting at the barrier
-    // below for its slowest warp (7.5 % of the kernel's stall samples)
+    // the warps draw their work units — one sample index of 32 triangles — from a block-wide counter: a static stride leaves the block
+    // waiting at the barrier below for its slowest warp (7.5 % of the kernel's stall samples at C-bunny), and with whole batches as units
+    // the 36 batches x 18 samples of C-arm on 32 warps left 31 % barrier stalls (the triangle is re-read per sample index: 5 % of a sample)
+    const unsigned nunits = (unsigned)((F + 31) / 32) * (unsigned)P.spp;
     for (;;) {
-      int base = 0;
-      if (lane == 0) base = (int)atomicAdd(&gs.next_batch, 32u);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= F) break;
+      unsigned u = 0u;
+      if (lane == 0) u = atomicAdd(&gs.next_batch, 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= nunits) break;
+      const int base = (int)(P.spp == 1 ? u : u / (unsigned)P.spp) * 32;
+      const int k = P.spp == 1 ? 0 : (int)(u % (unsigned)P.spp);
       const int p = base + lane;
       const bool active = p < F;
       TriRegs t; t.prim = 0;
@@ -530,10 +534,10 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
         }
       }
       if (__all_sync(0xffffffffu, culled)) {
-        if (WRITE_VIS && lane == 0) for (int k = 0; k < P.spp; ++k) vis[(size_t)(s * P.spp + k) * P.words_per_row + (base >> 5)] = 0u;
+        if (WRITE_VIS && lane == 0) vis[(size_t)(s * P.spp + k) * P.words_per_row + (base >> 5)] = 0u;
         continue;
       }
-      for (int k = 0; k < P.spp; ++k) {
+      {
         bool need = false; float val = 0.f, ts = 0.f; int bin = -1; f3 d = mk3(0.f, 0.f, 1.f);
         if (!culled) {
           SampleGeom g;
