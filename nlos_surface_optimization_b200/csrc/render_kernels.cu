@@ -724,7 +724,6 @@ __device__ __forceinline__ void group_trace(const DeviceScene& sc, const RenderP
   __syncwarp();
   const int G = gw.fr.G, K = gw.fr.K;
   const uint4* __restrict__ ent = reinterpret_cast<const uint4*>(gg.ent) + 2 * (size_t)(ent0 >> 2);      // blocks of 4 entries: [E0 E1 E2 E3][T0 T1 T2 T3]
-  const unsigned lt = (1u << lane) - 1u;
   const GGWalk wk = gg_ray_walk(gw.fr, r);
   const uint2* __restrict__ tab = gg.table + tab0;
   const float qmax = gw.fr.qmax;
