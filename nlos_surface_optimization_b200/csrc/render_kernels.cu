@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
     __syncthreads();
     const bool grid = gs.use_grid != 0;
     if (COUNT && tid == 0 && !grid) atomicAdd(scr.counters + 5, 1ull);
-    const PGridFrame fr = gs.fr;
+    const PGridFrame& fr = gs.fr;                 // read from shared memory where needed (a register copy of its 18 words spills)
     const int G = fr.G;
     // the warps draw their work units — one sample index of 32 triangles — from a block-wide counter: a static stride leaves the block
     // waiting at the barrier below for its slowest warp (7.5 % of the kernel's stall samples at C-bunny), and with whole batches as units
