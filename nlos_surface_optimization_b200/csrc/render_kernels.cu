@@ -18,6 +18,7 @@
 //
 // Reference: smoothed_transient/transient_and_gradient.cpp:122-237 (forward task), :843-1007 (gradient task),
 // :571-695 (albedo), :22-119 (intensity); ggx/transient_and_gradient.cpp:126-243, 385-512, 648-823.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include "nlos_ctx.h"
@@ -325,6 +326,40 @@ struct GridWarp {                          // per-warp scratch of pass 3
   unsigned occ;                            // bit l: the ray of lane l is occluded
   unsigned pad_[3];
 };
+#ifndef NLOS_GRID_SADDR
+#define NLOS_GRID_SADDR 15
+#endif
+#if NLOS_GRID_SADDR & 1
+// Pass 3 addresses the warp's scratch through ONE 32-bit shared-window address that went through a shuffle: ptxas otherwise
+// re-derives it (S2R SR_TID.X, S2R SR_CgaCtaId, shift, multiply-add) inside the exact-test and push loops instead of holding a register
+__device__ __forceinline__ unsigned lds_u(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void reds_or(unsigned a, unsigned v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+#define GW_F(field, i) lds_f(gwa + (unsigned)offsetof(GridWarp, field) + 4u * (unsigned)(i))
+#define GW_U(field, i) lds_u(gwa + (unsigned)offsetof(GridWarp, field) + 4u * (unsigned)(i))
+#define GW_OCC() lds_u(gwa + (unsigned)offsetof(GridWarp, occ))
+#define GW_SET_F(field, i, v) sts_f(gwa + (unsigned)offsetof(GridWarp, field) + 4u * (unsigned)(i), (v))
+#define GW_SET_U(field, i, v) sts_u(gwa + (unsigned)offsetof(GridWarp, field) + 4u * (unsigned)(i), (unsigned)(v))
+#define GW_SET_OCC(v) sts_u(gwa + (unsigned)offsetof(GridWarp, occ), (v))
+#define GW_OR_OCC(v) reds_or(gwa + (unsigned)offsetof(GridWarp, occ), (v))
+#else
+#define GW_F(field, i) gw.field[i]
+#define GW_U(field, i) ((unsigned)gw.field[i])
+#define GW_OCC() gw.occ
+#define GW_SET_F(field, i, v) gw.field[i] = (v)
+#define GW_SET_U(field, i, v) gw.field[i] = (v)
+#define GW_SET_OCC(v) gw.occ = (v)
+#define GW_OR_OCC(v) atomicOr(&gw.occ, (v))
+#endif
+// a block-uniform global pointer that went through a shuffle: ptxas holds it (in uniform registers) instead of re-deriving
+// base + blockIdx.x * stride (S2R, 64-bit multiply-add, LEA pair) at every access of the binning loops
+template <class T> __device__ __forceinline__ T* uniform_global_ptr(T* p) {
+  unsigned long long a = (unsigned long long)__cvta_generic_to_global(p);
+  a = __shfl_sync(0xffffffffu, a, 0);
+  return reinterpret_cast<T*>(__cvta_global_to_generic((size_t)a));
+}
 struct GridShared {
   PGridFrame fr;
   float zmin, pad_u, pad_v;
@@ -370,17 +405,35 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
                                                     uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
                                                     const GridScratch scr, unsigned cap, int G0, int Kz_arg) {
   const int Kz = KZT ? KZT : Kz_arg;
+#if NLOS_GRID_SADDR & 2     // experiment: the whole shared window addressed from a shuffled (= warp-uniform, not rematerialisable) base
+  extern __shared__ __align__(16) unsigned char smem_raw0[];
+  unsigned char* smem_raw = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic(__shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(smem_raw0), 0)));
+#else
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
   GridShared& gs = *reinterpret_cast<GridShared*>(smem_raw);
   double* s_w = reinterpret_cast<double*>(smem_raw + ((sizeof(GridShared) + 15) & ~size_t(15)));                  // SMOOTH: tap prefix sums
   GridWarp* gw_all = reinterpret_cast<GridWarp*>(reinterpret_cast<unsigned char*>(s_w) + (SMOOTH ? (((size_t)(P.K + 1) * sizeof(double) + 15) & ~size_t(15)) : 0));
   unsigned* cells = reinterpret_cast<unsigned*>(gw_all + kGridBlock / 32);
   if (SMOOTH) { for (int i = threadIdx.x; i <= P.K; i += kGridBlock) s_w[i] = wprefix[i]; }
+#if NLOS_GRID_SADDR & 4
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform to the compiler as well
+#else
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#endif
   GridWarp& gw = gw_all[warp];
+#if NLOS_GRID_SADDR & 1
+  const unsigned gwa = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(&gw), 0);
+#endif
+#if NLOS_GRID_SADDR & 8
+  float4* __restrict__ proj = uniform_global_ptr(scr.proj + (size_t)blockIdx.x * sc.V);
+  uint2* __restrict__ trect = uniform_global_ptr(scr.rect + (size_t)blockIdx.x * sc.F);
+  unsigned* __restrict__ ent = uniform_global_ptr(scr.ent + 2 * (size_t)blockIdx.x * cap);
+#else
   float4* __restrict__ proj = scr.proj + (size_t)blockIdx.x * sc.V;
   uint2* __restrict__ trect = scr.rect + (size_t)blockIdx.x * sc.F;
-  unsigned* __restrict__ ent = scr.ent + 2 * (size_t)blockIdx.x * cap;      // blocks of 4 entries (32 bytes): [E0 E1 E2 E3][T0 T1 T2 T3] — a candidate's triangle word sits in the sector its rectangle word was read from
+  unsigned* __restrict__ ent = scr.ent + 2 * (size_t)blockIdx.x * cap;
+#endif      // blocks of 4 entries (32 bytes): [E0 E1 E2 E3][T0 T1 T2 T3] — a candidate's triangle word sits in the sector its rectangle word was read from
   const float ub_half = P.ub / 2.0f, lb_half = P.lb / 2.0f;
   const int64_t nbf = (int64_t)P.numBins * P.r_fwd;
   const int F = sc.F;
@@ -574,14 +627,14 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
           }
           const uint4* __restrict__ lst = reinterpret_cast<const uint4*>(ent) + 2 * (size_t)(start >> 2);
           // the warp's rays, readable by every lane: the exact tests below are pooled over the warp
-          gw.dx[lane] = d.x; gw.dy[lane] = d.y; gw.dz[lane] = d.z; gw.ts[lane] = ts; gw.prim[lane] = t.prim;
-          if (lane == 0) gw.occ = 0u;
+          GW_SET_F(dx, lane, d.x); GW_SET_F(dy, lane, d.y); GW_SET_F(dz, lane, d.z); GW_SET_F(ts, lane, ts); GW_SET_U(prim, lane, t.prim);
+          if (lane == 0) GW_SET_OCC(0u);
           __syncwarp();
           const int maxg = __reduce_max_sync(0xffffffffu, ngrp);
           unsigned nhit = 0u;                                                     // work counter: cell-level check passes of this lane
           for (int g0 = 0; g0 < maxg; g0 += 8) {                                  // 32 entries per lane and round
             unsigned mask = 0u;
-            if (g0 < ngrp && !((gw.occ >> lane) & 1u)) {
+            if (g0 < ngrp && !((GW_OCC() >> lane) & 1u)) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (g0 + i < ngrp) {
@@ -606,23 +659,23 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
               // the pushing lane fetches the candidate's triangle index (up to kGridPush independent loads in flight) so that the exact-test
               // loop below starts with the triangle fetch instead of two dependent round trips
               // (the triangle word of entry b of this round: word 8 g0 + b + (b & ~3) + 4 of the list — same 32-byte sector as its rectangle word)
-              const unsigned* __restrict__ tw = reinterpret_cast<const unsigned*>(lst) + (8 * g0 + 4);
               const unsigned tag = (unsigned)lane << 27;
-              for (int i = 0; i < n; ++i) { const unsigned bpos = 31u - (unsigned)__clz(mask); mask ^= 1u << bpos; gw.pool[off + i] = tag | tw[bpos + (bpos & ~3u)]; }
+              const unsigned* __restrict__ tw = reinterpret_cast<const unsigned*>(lst) + (8 * g0 + 4);
+              for (int i = 0; i < n; ++i) { const unsigned bpos = 31u - (unsigned)__clz(mask); mask ^= 1u << bpos; GW_SET_U(pool, off + i, tag | tw[bpos + (bpos & ~3u)]); }
               __syncwarp();
               for (int i = lane; i < total; i += 32) {
-                const unsigned item = gw.pool[i];
+                const unsigned item = GW_U(pool, i);
                 const int rl = (int)(item >> 27);
-                if (!((gw.occ >> rl) & 1u)) {
+                if (!((GW_OCC() >> rl) & 1u)) {
                   const int tj = (int)(item & 0x7ffffffu);
-                  if (tj != base + rl && tri_occludes_od(sc.ttris, tj, o, mk3(gw.dx[rl], gw.dy[rl], gw.dz[rl]), gw.ts[rl], gw.prim[rl])) atomicOr(&gw.occ, 1u << rl);
+                  if (tj != base + rl && tri_occludes_od(sc.ttris, tj, o, mk3(GW_F(dx, rl), GW_F(dy, rl), GW_F(dz, rl)), GW_F(ts, rl), (int)GW_U(prim, rl))) GW_OR_OCC(1u << rl);
                 }
               }
               __syncwarp();
             }
           }
           __syncwarp();
-          occ = occ || ((gw.occ >> lane) & 1u);
+          occ = occ || ((GW_OCC() >> lane) & 1u);
           __syncwarp();                                                             // gw is rewritten by the next sample
           if (COUNT) {                                                              // measurement instantiation only (bench.py roofline.executed)
             const unsigned c1 = __reduce_add_sync(0xffffffffu, need ? 1u : 0u), c2 = __reduce_add_sync(0xffffffffu, (unsigned)(4 * ngrp)), c3 = __reduce_add_sync(0xffffffffu, nhit);
@@ -929,9 +982,12 @@ __global__ void k_box_filter(const double* __restrict__ in, double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- K4/K5 gradients
+#ifndef NLOS_GRAD_MINBLOCKS
+#define NLOS_GRAD_MINBLOCKS 1
+#endif
 // KIND 0: vertex gradient (9 FP64 register accumulators per thread), 1: albedo scalar, 2: GGX alpha scalar
 template <bool GGX, bool HAS_VN, bool HAS_VA, int KIND, bool USE_VIS>
-__global__ void __launch_bounds__(kBlock) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
+__global__ void __launch_bounds__(kBlock, NLOS_GRAD_MINBLOCKS) k_gradient(const DeviceScene sc, const RenderParams P, const double* __restrict__ diff,
                                                      const uint32_t* __restrict__ vis, const double* __restrict__ wprefix,
                                                      const double* __restrict__ dprefix, double* __restrict__ out) {
   extern __shared__ double s_tab[];         // [0..K] prefix of w_i, [K+1..2K+1] prefix of w_i*delta_i
@@ -1272,6 +1328,9 @@ void launch_forward_group_t(Ctx& cx, const DeviceScene& sc, const RenderParams& 
 
 template <bool GGX, bool VN, bool VA, bool SMOOTH, int MODE>
 void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, double* out, uint32_t* vis, const double* wprefix) {
+#ifdef NLOS_QUICK_BUILD      // kernel experiments only (tools/build_variant.sh): the headline instantiation of the per-point grid kernel and nothing else
+  launch_forward_grid_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return;
+#else
   if (use_group_forward(cx, sc, P)) { launch_forward_group_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
   if (use_grid_forward(cx, sc, P)) { launch_forward_grid_t<GGX, VN, VA, SMOOTH, MODE>(cx, sc, P, out, vis, wprefix); return; }
   cx.last_forward_algo = 1; cx.last_grid_res = 0;
@@ -1285,6 +1344,7 @@ void launch_forward_t(Ctx& cx, const DeviceScene& sc, const RenderParams& P, dou
   if (vis) k_forward<GGX, VN, VA, SMOOTH, true, MODE><<<grid, kFwdBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   else k_forward<GGX, VN, VA, SMOOTH, false, MODE><<<grid, kFwdBlock, smem, cx.stream>>>(sc, P, out, vis, wprefix);
   cx.launches += 1;
+#endif
 }
 
 template <bool GGX, bool VN, bool VA, int KIND>
@@ -1308,6 +1368,10 @@ void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool 
   if (sc.F <= 0 || P.L <= 0) return;
   const bool vn = sc.vnormal != nullptr, va = sc.valbedo != nullptr, sm = P.r_fwd > 1;
 #define NLOS_FWD(G, N, A, S) launch_forward_t<G, N, A, S, 0>(cx, sc, P, transient, vis, wprefix)
+#ifdef NLOS_QUICK_BUILD
+  if (ggx || vn || va || sm) std::abort();
+  NLOS_FWD(false, false, false, false);
+#else
   if (!ggx) {
     if (!vn && !va) { if (sm) NLOS_FWD(false, false, false, true); else NLOS_FWD(false, false, false, false); }
     else if (vn && !va) { if (sm) NLOS_FWD(false, true, false, true); else NLOS_FWD(false, true, false, false); }
@@ -1319,6 +1383,7 @@ void launch_forward(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool 
     else if (!vn && va) { if (sm) NLOS_FWD(true, false, true, true); else NLOS_FWD(true, false, true, false); }
     else { if (sm) NLOS_FWD(true, true, true, true); else NLOS_FWD(true, true, true, false); }
   }
+#endif
 #undef NLOS_FWD
   NLOS_CUDA_OK(cudaGetLastError());
 }
@@ -1328,8 +1393,12 @@ int forward_max_chunk() { return kTile; }      // sample slots per warp pass of 
 void launch_intensity(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool ggx, double* intensity) {
   if (sc.F <= 0 || P.L <= 0) return;
   const bool vn = sc.vnormal != nullptr;
+#ifdef NLOS_QUICK_BUILD
+  std::abort();
+#else
   if (!ggx) { if (vn) launch_forward_t<false, true, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); else launch_forward_t<false, false, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); }
   else { if (vn) launch_forward_t<true, true, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); else launch_forward_t<true, false, false, false, 1>(cx, sc, P, intensity, nullptr, nullptr); }
+#endif
   NLOS_CUDA_OK(cudaGetLastError());
 }
 
@@ -1352,6 +1421,10 @@ void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool
   if (sc.F <= 0 || P.L <= 0) return;
   const bool vn = sc.vnormal != nullptr, va = sc.valbedo != nullptr;
 #define NLOS_GRAD(G, N, A, KD) launch_gradient_t<G, N, A, KD>(cx, sc, P, diff, vis, wprefix, dprefix, out)
+#ifdef NLOS_QUICK_BUILD
+  if (kind != 0 || ggx || vn || va) std::abort();
+  NLOS_GRAD(false, false, false, 0);
+#else
   if (kind == 0) {
     if (!ggx) {
       if (!vn && !va) NLOS_GRAD(false, false, false, 0); else if (vn && !va) NLOS_GRAD(false, true, false, 0);
@@ -1367,6 +1440,7 @@ void launch_gradient(Ctx& cx, const DeviceScene& sc, const RenderParams& P, bool
     if (!vn && !va) NLOS_GRAD(true, false, false, 2); else if (vn && !va) NLOS_GRAD(true, true, false, 2);
     else if (!vn && va) NLOS_GRAD(true, false, true, 2); else NLOS_GRAD(true, true, true, 2);
   }
+#endif
 #undef NLOS_GRAD
   NLOS_CUDA_OK(cudaGetLastError());
 }
