@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
       for (int p = b; p < e; ++p) {
         bool dead = false;
         if (do_cull) {
-          const float4 s0 = __ldg(sc.stris + 4 * (size_t)p), s1 = __ldg(sc.stris + 4 * (size_t)p + 1), s2 = __ldg(sc.stris + 4 * (size_t)p + 2), s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+          const float4 s0 = __ldg(sc.stris + p), s1 = __ldg(sc.stris + 1 * (size_t)sc.F + p), s2 = __ldg(sc.stris + 2 * (size_t)sc.F + p), s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
           const f3 nf = mk3(s1.w, s2.w, s3.x);
           const f3 w1 = xyz(s0) - c, w2 = xyz(s1) - c, w3 = xyz(s2) - c;
           const float nf_inf = fmaxf(fabsf(nf.x), fmaxf(fabsf(nf.y), fabsf(nf.z)));
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
         else {                                                                   // (runs longer than 64: F > 65536 — evaluate again)
           dead = false;
           if (do_cull) {
-            const float4 s0 = __ldg(sc.stris + 4 * (size_t)p), s1 = __ldg(sc.stris + 4 * (size_t)p + 1), s2 = __ldg(sc.stris + 4 * (size_t)p + 2), s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+            const float4 s0 = __ldg(sc.stris + p), s1 = __ldg(sc.stris + 1 * (size_t)sc.F + p), s2 = __ldg(sc.stris + 2 * (size_t)sc.F + p), s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
             const f3 nf = mk3(s1.w, s2.w, s3.x);
             const f3 w1 = xyz(s0) - c, w2 = xyz(s1) - c, w3 = xyz(s2) - c;
             const float nf_inf = fmaxf(fabsf(nf.x), fmaxf(fabsf(nf.y), fabsf(nf.z)));
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
       __syncthreads();
       unsigned mine = 0u;
       for (int p = tid; p < F; p += kBinBlock) {
-        const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+        const float4 s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
         const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
         int a0, a1, b0, b1, k0, k1; float wlo, whi;
         gg_tri_box(fr, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z, a0, a1, b0, b1, k0, k1, wlo, whi);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kBinBlock, 1) k_group_bin(const DeviceScene sc
       if (total <= (unsigned long long)cap) {
         if (smem_counts) { __syncthreads(); for (int i = tid; i < (ncell + 1) / 2; i += kBinBlock) cnt16[i] = 0u; __syncthreads(); }
         for (int p = tid; p < F; p += kBinBlock) {
-          const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+          const float4 s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
           const float4 p1 = proj[__float_as_int(s3.y)], p2 = proj[__float_as_int(s3.z)], p3 = proj[__float_as_int(s3.w)];
           int a0, a1, b0, b1, k0, k1; float wlo, whi;
           gg_tri_box(fr, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z, a0, a1, b0, b1, k0, k1, wlo, whi);

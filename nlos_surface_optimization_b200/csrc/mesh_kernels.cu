@@ -21,10 +21,10 @@ __global__ void k_vertex_gradient(const DeviceScene sc, const RenderParams P, in
                                   double sigma2, double* __restrict__ acc /*[B,3]*/) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= sc.F) return;
-  const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+  const float4 s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
   const int i1 = __float_as_int(s3.y), i2 = __float_as_int(s3.z), i3 = __float_as_int(s3.w);
   if (i1 != vertex_num && i2 != vertex_num && i3 != vertex_num) return;                  // TG.cpp:729-731
-  const float4 s0 = __ldg(sc.stris + 4 * (size_t)p), s1 = __ldg(sc.stris + 4 * (size_t)p + 1), s2 = __ldg(sc.stris + 4 * (size_t)p + 2);
+  const float4 s0 = __ldg(sc.stris + p), s1 = __ldg(sc.stris + 1 * (size_t)sc.F + p), s2 = __ldg(sc.stris + 2 * (size_t)sc.F + p);
   ShadeTri st; st.v1 = xyz(s0); st.A = s0.w; st.v2 = xyz(s1); st.v3 = xyz(s2); st.nf = mk3(s1.w, s2.w, s3.x); st.i1 = i1; st.i2 = i2; st.i3 = i3;
   const float4 q0 = __ldg(sc.ttris + 4 * (size_t)p), q1 = __ldg(sc.ttris + 4 * (size_t)p + 1), q2 = __ldg(sc.ttris + 4 * (size_t)p + 2), q3 = __ldg(sc.ttris + 4 * (size_t)p + 3);
   TriRec tr; tr.v0 = xyz(q0); tr.e1 = xyz(q1); tr.e2 = xyz(q2); tr.Ng = xyz(q3); const int prim = __float_as_int(q0.w);

@@ -16,7 +16,8 @@ struct DeviceScene {
   int F = 0, V = 0;
   int root_count = 0;           // >0: the whole mesh is one leaf run (F <= kLeafMax)
   const float4* ttris = nullptr;   // [F][4]  TraceTri
-  const float4* stris = nullptr;   // [F][4]  ShadeTri
+  const float4* stris = nullptr;   // [4][F]  ShadeTri, component-major: (v1,A) (v2,nf.x) (v3,nf.y) (nf.z,i1,i2,i3)
+  const int* sprim = nullptr;      // [F]     caller's index of the triangle at Morton position p (== ttris[4p].w)
   const BvhNode* nodes = nullptr;  // [max(F-1,1)]
   const float* vnormal = nullptr;  // [V,3] or null (caller order)
   const float* valbedo = nullptr;  // [V]   or null

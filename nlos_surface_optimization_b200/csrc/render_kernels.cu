@@ -45,11 +45,11 @@ struct TriRegs {
 
 template <bool HAS_VN, bool HAS_VA>
 __device__ __forceinline__ void load_tri(const DeviceScene& sc, int p, TriRegs& t) {
-  const float4 s0 = __ldg(sc.stris + 4 * (size_t)p), s1 = __ldg(sc.stris + 4 * (size_t)p + 1), s2 = __ldg(sc.stris + 4 * (size_t)p + 2), s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+  const float4 s0 = __ldg(sc.stris + p), s1 = __ldg(sc.stris + 1 * (size_t)sc.F + p), s2 = __ldg(sc.stris + 2 * (size_t)sc.F + p), s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
   t.st.v1 = xyz(s0); t.st.A = s0.w; t.st.v2 = xyz(s1); t.st.v3 = xyz(s2); t.st.nf = mk3(s1.w, s2.w, s3.x);
   t.st.i1 = __float_as_int(s3.y); t.st.i2 = __float_as_int(s3.z); t.st.i3 = __float_as_int(s3.w);
   const float4 q0 = __ldg(sc.ttris + 4 * (size_t)p), q1 = __ldg(sc.ttris + 4 * (size_t)p + 1), q2 = __ldg(sc.ttris + 4 * (size_t)p + 2), q3 = __ldg(sc.ttris + 4 * (size_t)p + 3);
-  t.tr.v0 = xyz(q0); t.tr.e1 = xyz(q1); t.tr.e2 = xyz(q2); t.tr.Ng = xyz(q3); t.prim = __float_as_int(q0.w);
+  t.tr.v0 = xyz(q0); t.tr.e1 = xyz(q1); t.tr.e2 = xyz(q2); t.tr.Ng = xyz(q3); t.prim = __ldg(sc.sprim + p);     // (not q0.w: a kernel that does not use t.tr then loads no trace record at all)
   if (HAS_VN) {
     const float* vn = sc.vnormal;
     t.n1 = mk3(__ldg(vn + 3 * (size_t)t.st.i1), __ldg(vn + 3 * (size_t)t.st.i1 + 1), __ldg(vn + 3 * (size_t)t.st.i1 + 2));
@@ -500,15 +500,15 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
         int p = tid;
         float4 s3n = make_float4(0.f, 0.f, 0.f, 0.f), q1 = s3n, q2 = s3n, q3 = s3n;
         if (p < F) {
-          const float4 s3 = __ldg(sc.stris + 4 * (size_t)p + 3);
+          const float4 s3 = __ldg(sc.stris + 3 * (size_t)sc.F + p);
           q1 = proj[__float_as_int(s3.y)]; q2 = proj[__float_as_int(s3.z)]; q3 = proj[__float_as_int(s3.w)];
-          if (p + kGridBlock < F) s3n = __ldg(sc.stris + 4 * (size_t)(p + kGridBlock) + 3);
+          if (p + kGridBlock < F) s3n = __ldg(sc.stris + 3 * (size_t)sc.F + (p + kGridBlock));
         }
         for (; p < F; p += kGridBlock) {
           const float4 p1 = q1, p2 = q2, p3 = q3;
           if (p + kGridBlock < F) {
             q1 = proj[__float_as_int(s3n.y)]; q2 = proj[__float_as_int(s3n.z)]; q3 = proj[__float_as_int(s3n.w)];
-            if (p + 2 * kGridBlock < F) s3n = __ldg(sc.stris + 4 * (size_t)(p + 2 * kGridBlock) + 3);
+            if (p + 2 * kGridBlock < F) s3n = __ldg(sc.stris + 3 * (size_t)sc.F + (p + 2 * kGridBlock));
           }
           int a0, a1, b0, b1;
           pg_tri_rect(fr, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, pad_u, pad_v, a0, a1, b0, b1);
@@ -983,7 +983,7 @@ __global__ void k_box_filter(const double* __restrict__ in, double* __restrict__
 
 // ---------------------------------------------------------------------------------------------- K4/K5 gradients
 #ifndef NLOS_GRAD_MINBLOCKS
-#define NLOS_GRAD_MINBLOCKS 1
+#define NLOS_GRAD_MINBLOCKS 7      // <= 72 registers, 28 warps per SM: measured 1 (125 registers) 4.25 ms, 5 4.15, 6 4.11, 7 4.02, 8 4.04 @C-bunny; GGX + shading normals 7.24 -> 5.83
 #endif
 // KIND 0: vertex gradient (9 FP64 register accumulators per thread), 1: albedo scalar, 2: GGX alpha scalar
 template <bool GGX, bool HAS_VN, bool HAS_VA, int KIND, bool USE_VIS>
