@@ -651,16 +651,16 @@ __global__ void __launch_bounds__(kGridBlock, NLOS_GRID_MINBLOCKS) k_forward_gri
             while (__any_sync(0xffffffffu, mask != 0u)) {
               const int nb = __popc(mask);
               const int n = nb < kGridPush ? nb : kGridPush;
-              int incl = n;
-#pragma unroll
-              for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += y; }
-              const int total = __shfl_sync(0xffffffffu, incl, 31);
-              int off = incl - n;
               // the pushing lane fetches the candidate's triangle index (up to kGridPush independent loads in flight) so that the exact-test
               // loop below starts with the triangle fetch instead of two dependent round trips
               // (the triangle word of entry b of this round: word 8 g0 + b + (b & ~3) + 4 of the list — same 32-byte sector as its rectangle word)
               const unsigned tag = (unsigned)lane << 27;
               const unsigned* __restrict__ tw = reinterpret_cast<const unsigned*>(lst) + (8 * g0 + 4);
+              int incl = n;
+#pragma unroll
+              for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o2); if (lane >= o2) incl += y; }
+              const int total = __shfl_sync(0xffffffffu, incl, 31);
+              int off = incl - n;
               for (int i = 0; i < n; ++i) { const unsigned bpos = 31u - (unsigned)__clz(mask); mask ^= 1u << bpos; GW_SET_U(pool, off + i, tag | tw[bpos + (bpos & ~3u)]); }
               __syncwarp();
               for (int i = lane; i < total; i += 32) {
