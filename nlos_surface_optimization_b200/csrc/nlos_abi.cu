@@ -121,14 +121,15 @@ struct Job {
 };
 
 // gradient kernel: sources per block (blockIdx.y).  The default (128) amortises the 9 atomics per (triangle, chunk); small meshes
-// get a smaller chunk so that the grid still fills the machine (F = 1125: 9 x 32 = 288 blocks on 148 SMs x 4 -> 9 x 133).
+// get a smaller chunk so that the grid is MANY waves of the 148 x 7 resident blocks, not one and a bit (F = 1125, L = 4096: chunk 31 -> 1197
+// blocks = 1.16 waves 2.79 ms; chunk 8 -> 4608 blocks 2.31 ms; chunk 4 -> 9216 blocks 2.24 ms; tools/sweep_chunk.py).
 int auto_chunk(const Ctx& cx, const char* key, int F, int64_t L, int dflt) {
   (void)key;
   int c = dflt;
   if (cx.chunk_gradient <= 0) {
-    const int64_t nx = ((int64_t)F + 127) / 128, target = 148 * 8;      // 128 = threads per block of k_gradient
+    const int64_t nx = ((int64_t)F + 127) / 128, target = 148 * 7 * 8;  // 128 = threads per block of k_gradient, 7 resident blocks per SM, 8 waves
     const int64_t ny = (target + nx - 1) / nx;
-    const int64_t fit = std::max<int64_t>(8, L / std::max<int64_t>(ny, 1));
+    const int64_t fit = std::max<int64_t>(4, L / std::max<int64_t>(ny, 1));
     if (fit < c) c = (int)fit;
   }
   if ((int64_t)c > L) c = (int)std::max<int64_t>(L, 1);
