@@ -1019,7 +1019,10 @@ __global__ void __launch_bounds__(kBlock, NLOS_GRAD_MINBLOCKS) k_gradient(const 
       if (sl < slotB && warp_global * 32 < sc.F) myword = __ldg(vis + (size_t)sl * P.words_per_row + warp_global);
     }
     const int cnt = (int)(slotB - base < 32 ? slotB - base : 32);
-    for (int i = 0; i < cnt; ++i) {
+    // only the slots in which some lane of the warp has a visible sample (lane l holds the word of slot base + l): 4.01 -> 3.91 ms @C-bunny
+    unsigned todo = USE_VIS ? __ballot_sync(0xffffffffu, myword != 0u) : (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+    while (todo) {
+      const int i = __ffs(todo) - 1; todo &= todo - 1u;
       const int64_t slot = base + i;
       const int64_t s = P.spp == 1 ? slot : slot / P.spp;
       const int k = P.spp == 1 ? 0 : (int)(slot - s * P.spp);
