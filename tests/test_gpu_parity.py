@@ -600,3 +600,29 @@ def test_many_samples_per_triangle(spp, oracle, gpu_ctx):
     Ts = np.zeros_like(T)
     renderer.renderStreamedTransient(o, n, v, f, ns, LB, UB, RES, Ts, pl, 10, 2, ctx=gpu_ctx)
     assert rel_l2(Ts, Ts_ref) <= TOL_TRANSIENT
+
+
+@pytest.mark.parametrize('reuse', [1, 0])
+def test_gradient_chunk_sizes_agree(reuse, oracle, gpu_ctx):
+    """Sources per block of the gradient kernel (option chunk_gradient; 0 = automatic, small meshes get small chunks): any chunk — also ones
+    that leave a partial group of 32 sample slots at the end of a block, with spp > 1 — gives the same gradient, against the oracle and among
+    themselves, with the forward pass's visibility words (only the slots with a visible lane are walked) and when re-tracing."""
+    from nlos_surface_optimization_b200 import renderer, scenes
+    v, f = scenes.icosphere(3, 0.1, (0.01, -0.02, 0.45), noise=0.03, seed=5); o, n = scenes.wall_grid(7)       # 49 wall points
+    ns = 3 * f.shape[0]                                                                                       # spp = 3: 147 slots
+    data, weight = make_target(oracle, o, n, v, f, ns)
+    T_ref, G_ref, _ = oracle.gradient(o, n, v, f, ns, LB, UB, RES, data, weight, 10, 1)
+    B = T_ref.shape[1]
+    gpu_ctx.set_option('reuse_visibility', reuse)
+    out = []
+    try:
+        for chunk in (0, 1, 4, 13, 37, 128):
+            gpu_ctx.set_option('chunk_gradient', chunk)
+            T = np.zeros((o.shape[0], B)); pl = np.zeros(B); G = np.zeros((v.shape[0], 3))
+            renderer.renderStreamedGradient(o, n, v, f, ns, LB, UB, RES, T, pl, G, data, weight, 10, 1, 1, 0, ctx=gpu_ctx)
+            assert rel_l2(G, G_ref) <= TOL_GRADIENT
+            out.append(G)
+    finally:
+        gpu_ctx.set_option('chunk_gradient', 0); gpu_ctx.set_option('reuse_visibility', 1)
+    for G in out[1:]:
+        assert rel_l2(G, out[0]) <= 1e-12
