@@ -13,4 +13,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_reference.
 bash tools/capture_profiles.sh $T
 rm -f $O/${T}_full.ncu-rep
 for tool in memcheck racecheck initcheck; do timeout 900 compute-sanitizer --tool $tool python tools/sanitize_small.py > $O/${T}_sanitize_$tool.log 2>&1; done
-tail -2 $O/${T}_pytest_gpu.log; cat $O/${T}_smoke.log | tail -1; for f in bench bench_ggx bench_arm bench_scale bench_reference; do python -c "import json,sys; d=json.loads(open('$O/${T}_$f.json').read().strip().splitlines()[-1]); print('$f', d.get('ms_per_step'), d.get('value'), (d.get('roofline') or {}).get('frac'))"; done; tail -2 $O/${T}_sanitize_*.log
+tail -2 $O/${T}_pytest_gpu.log; cat $O/${T}_smoke.log | tail -1; for f in bench bench_ggx bench_arm bench_scale bench_reference; do python -c "import json,sys; d=json.loads(open('$O/${T}_$f.json').read().strip().splitlines()[-1]); print('$f', d.get('ms_per_step'), d.get('value'), (d.get('roofline') or {}).get('frac'))"; done; for t in memcheck racecheck initcheck; do tail -n 1 $O/${T}_sanitize_$t.log; done
